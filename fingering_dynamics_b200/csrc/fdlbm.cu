@@ -1,0 +1,538 @@
+// fdlbm.cu -- host side of the C ABI declared in include/fdlbm.h (engine life cycle, layout
+// conversion, step scheduling).  Kernels live in lbm_kernels.cuh / lbm_fused.cuh.
+#include "../../include/fdlbm.h"
+
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "lbm_kernels.cuh"
+#include "lbm_fused.cuh"
+
+using namespace fdlbm;
+
+namespace {
+
+thread_local std::string g_err;
+
+int fail(int code, const char *fmt, ...)
+{
+    char buf[512];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof buf, fmt, ap);
+    va_end(ap);
+    g_err = buf;
+    return code;
+}
+
+#define CU(call)                                                                                      \
+    do {                                                                                              \
+        cudaError_t _e = (call);                                                                      \
+        if (_e != cudaSuccess)                                                                        \
+            return fail(FDLBM_E_CUDA, "%s failed: %s (%s:%d)", #call, cudaGetErrorString(_e), __FILE__, \
+                        __LINE__);                                                                    \
+    } while (0)
+
+enum { ST_EMPTY = 0, ST_PRE = 1, ST_POST = 2 };
+
+}  // namespace
+
+struct fdlbm_engine {
+    fdlbm_config cfg{};
+    int Wl = 0, Hp = 0, ncols = 0;
+    size_t esize = 8;
+    void *lat[2] = {nullptr, nullptr};
+    void *psi[2] = {nullptr, nullptr};
+    void *fields = nullptr;  // 9 planes of ncols*Hp reals: rho ux uy p mu mix_tau gx gy lap
+    uint8_t *reflect = nullptr, *solid_bytes = nullptr;
+    uint32_t *solid = nullptr;
+    void *inlet = nullptr, *outlet = nullptr;
+    void *staging = nullptr;
+    size_t staging_bytes = 0;
+    cudaStream_t stream = nullptr;
+    int cur = 0, pcur = 0;
+    int state = ST_EMPTY;
+    bool have_geometry = false;
+    int64_t iters = 0;
+    int64_t launches = 0;
+    int kernel = FDLBM_KERNEL_FUSED;
+
+    size_t lat_elems() const { return (size_t)ncols * NPOP * Hp; }
+    size_t plane_elems() const { return (size_t)ncols * Hp; }
+    bool has_lo() const { return cfg.x0 > 0 || cfg.x_periodic; }
+    bool has_hi() const { return cfg.x1 < cfg.W || cfg.x_periodic; }
+};
+
+namespace {
+
+template <typename T>
+LbmParams<T> make_params(const fdlbm_engine *e, int src, int psrc)
+{
+    const fdlbm_config &c = e->cfg;
+    LbmParams<T> P;
+    P.src = (const T *)e->lat[src];
+    P.dst = (T *)e->lat[1 - src];
+    P.reflect = e->reflect;
+    P.solid = e->solid;
+    P.psi_old = (const T *)e->psi[psrc];
+    P.psi_new = (T *)e->psi[1 - psrc];
+    P.inlet_ux = (const T *)e->inlet;
+    P.outlet_ux = (const T *)e->outlet;
+    P.H = c.H;
+    P.Hp = e->Hp;
+    P.Wl = e->Wl;
+    P.gx0 = c.x0;
+    P.W = c.W;
+    P.y_wall = c.psi_y_wall;
+    P.x_periodic = c.x_periodic;
+    P.zou_he = c.zou_he;
+    P.inv_tau = (T)(1.0 / c.tau);
+    P.gamma = (T)c.gamma;
+    P.a = (T)c.a;
+    P.kappa = (T)c.kappa;
+    P.eta6m = (T)(6.0 * c.Eta_n * c.M);
+    P.M = (T)c.M;
+    P.psi_wall = (T)c.psi_wall;
+    P.psi_left = (T)c.psi_left;
+    P.psi_right = (T)c.psi_right;
+    P.f3coef = (T)c.outlet_f3_coef;
+    return P;
+}
+
+template <typename T>
+FieldPtrs<T> field_ptrs(const fdlbm_engine *e)
+{
+    T *b = (T *)e->fields;
+    const size_t n = e->plane_elems();
+    FieldPtrs<T> F;
+    F.rho = b;
+    F.ux = b + n;
+    F.uy = b + 2 * n;
+    F.p = b + 3 * n;
+    F.mu = b + 4 * n;
+    F.mix_tau = b + 5 * n;
+    F.gx = b + 6 * n;
+    F.gy = b + 7 * n;
+    F.lap = b + 8 * n;
+    return F;
+}
+
+int ensure_staging(fdlbm_engine *e, size_t bytes)
+{
+    if (bytes <= e->staging_bytes) return 0;
+    if (e->staging) cudaFree(e->staging);
+    e->staging = nullptr;
+    e->staging_bytes = 0;
+    CU(cudaMalloc(&e->staging, bytes));
+    e->staging_bytes = bytes;
+    return 0;
+}
+
+int ensure_fields(fdlbm_engine *e)
+{
+    if (e->fields) return 0;
+    CU(cudaMalloc(&e->fields, 9 * e->plane_elems() * e->esize));
+    CU(cudaMemsetAsync(e->fields, 0, 9 * e->plane_elems() * e->esize, e->stream));
+    return 0;
+}
+
+dim3 cell_grid(const fdlbm_engine *e, int ncol) { return dim3((e->cfg.H + TPB - 1) / TPB, ncol); }
+
+// local periodic wrap of the two ghost columns per side (single slab spanning the whole x range)
+int wrap_ghosts(fdlbm_engine *e, void *lat)
+{
+    const size_t col = (size_t)NPOP * e->Hp * e->esize;
+    char *b = (char *)lat;
+    CU(cudaMemcpyAsync(b, b + (size_t)e->Wl * col, 2 * col, cudaMemcpyDeviceToDevice, e->stream));
+    CU(cudaMemcpyAsync(b + (size_t)(e->Wl + G) * col, b + (size_t)G * col, 2 * col, cudaMemcpyDeviceToDevice,
+                       e->stream));
+    return 0;
+}
+
+template <typename T>
+int launch_step(fdlbm_engine *e, bool finalize)
+{
+    LbmParams<T> P = make_params<T>(e, e->cur, e->pcur);
+    if (e->cfg.x_periodic && !e->cfg.external_halo) {
+        int rc = wrap_ghosts(e, e->lat[e->cur]);
+        if (rc) return rc;
+    }
+    const int lo = e->has_lo() ? -1 : 0, hi = e->Wl + (e->has_hi() ? 1 : 0);
+    if (finalize || e->kernel == FDLBM_KERNEL_TWOPASS) {
+        k_psi<T><<<cell_grid(e, hi - lo), TPB, 0, e->stream>>>(P, lo);
+        if (finalize)
+            k_step_twopass<T, true><<<cell_grid(e, e->Wl), TPB, 0, e->stream>>>(P, field_ptrs<T>(e));
+        else
+            k_step_twopass<T, false><<<cell_grid(e, e->Wl), TPB, 0, e->stream>>>(P, field_ptrs<T>(e));
+        e->launches += 2;
+    } else {
+        int rc = launch_fused<T>(P, e->stream);
+        if (rc) return fail(FDLBM_E_CUDA, "fused launch configuration failed (%d)", rc);
+        e->launches += 1;
+    }
+    CU(cudaGetLastError());
+    return 0;
+}
+
+template <typename T>
+int do_steps(fdlbm_engine *e, int n)
+{
+    if (n <= 0) return 0;
+    if (e->state == ST_PRE) {
+        // first collision from the caller's macroscopic arrays, in place on lat[cur]
+        LbmParams<T> P = make_params<T>(e, 1 - e->cur, e->pcur);  // dst = lat[cur]
+        k_collide_first<T><<<cell_grid(e, e->Wl), TPB, 0, e->stream>>>(P, field_ptrs<T>(e), (const T *)e->psi[e->pcur]);
+        CU(cudaGetLastError());
+        e->launches += 1;
+        e->state = ST_POST;
+        e->iters += 1;
+        n -= 1;
+    }
+    for (int k = 0; k < n; ++k) {
+        int rc = launch_step<T>(e, false);
+        if (rc) return rc;
+        e->cur ^= 1;
+        e->pcur ^= 1;
+        e->iters += 1;
+    }
+    return 0;
+}
+
+// host (H, ncw) window <-> device, for one plane family
+struct Overlap {
+    int lo, n;  // global columns [lo, lo+n) = window ∩ slab
+};
+Overlap overlap(const fdlbm_engine *e, int col0, int ncols)
+{
+    const int lo = col0 > e->cfg.x0 ? col0 : e->cfg.x0;
+    const int hi = (col0 + ncols) < e->cfg.x1 ? (col0 + ncols) : e->cfg.x1;
+    return Overlap{lo, hi > lo ? hi - lo : 0};
+}
+
+template <typename T>
+int upload_planes(fdlbm_engine *e, const double *host, int nplanes, int col0, int ncw, T *base, size_t plane_stride,
+                  size_t xstride)
+{
+    const Overlap ov = overlap(e, col0, ncw);
+    if (!ov.n) return 0;
+    const int H = e->cfg.H;
+    int rc = ensure_staging(e, (size_t)nplanes * H * ov.n * sizeof(double));
+    if (rc) return rc;
+    CU(cudaMemcpy2DAsync(e->staging, (size_t)ov.n * sizeof(double), host + (ov.lo - col0), (size_t)ncw * sizeof(double),
+                         (size_t)ov.n * sizeof(double), (size_t)nplanes * H, cudaMemcpyHostToDevice, e->stream));
+    const int xl_lo = ov.lo - e->cfg.x0, xl_hi = xl_lo + ov.n;
+    dim3 grid((ov.n + 31) / 32, (H + 31) / 32), block(32, 8);
+    for (int k = 0; k < nplanes; ++k) {
+        k_transpose_in<double, T><<<grid, block, 0, e->stream>>>((const double *)e->staging + (size_t)k * H * ov.n, H, ov.n,
+                                                                  ov.lo, base + k * plane_stride, xstride, xl_lo, xl_hi,
+                                                                  e->cfg.x0, e->cfg.W, 0);
+        e->launches += 1;
+    }
+    CU(cudaGetLastError());
+    // the staging buffer is reused by the next upload: serialise
+    CU(cudaStreamSynchronize(e->stream));
+    return 0;
+}
+
+template <typename T>
+int download_planes(fdlbm_engine *e, double *host, int nplanes, int col0, int ncw, const T *base, size_t plane_stride,
+                    size_t xstride)
+{
+    if (!host) return 0;
+    const Overlap ov = overlap(e, col0, ncw);
+    if (!ov.n) return 0;
+    const int H = e->cfg.H;
+    int rc = ensure_staging(e, (size_t)nplanes * H * ov.n * sizeof(double));
+    if (rc) return rc;
+    const int xl_lo = ov.lo - e->cfg.x0, xl_hi = xl_lo + ov.n;
+    dim3 grid((ov.n + 31) / 32, (H + 31) / 32), block(32, 8);
+    for (int k = 0; k < nplanes; ++k) {
+        k_transpose_out<T, double><<<grid, block, 0, e->stream>>>(base + k * plane_stride, xstride, xl_lo, xl_hi, e->cfg.x0,
+                                                                   (double *)e->staging + (size_t)k * H * ov.n, H, ov.n,
+                                                                   ov.lo);
+        e->launches += 1;
+    }
+    CU(cudaGetLastError());
+    CU(cudaMemcpy2DAsync(host + (ov.lo - col0), (size_t)ncw * sizeof(double), e->staging, (size_t)ov.n * sizeof(double),
+                         (size_t)ov.n * sizeof(double), (size_t)nplanes * H, cudaMemcpyDeviceToHost, e->stream));
+    CU(cudaStreamSynchronize(e->stream));
+    return 0;
+}
+
+template <typename T>
+int set_state_t(fdlbm_engine *e, int col0, int ncw, const fdlbm_fields *in)
+{
+    const size_t Hp = e->Hp, n = e->plane_elems();
+    int rc = ensure_fields(e);
+    if (rc) return rc;
+    e->cur = 0;
+    e->pcur = 0;
+    CU(cudaMemsetAsync(e->lat[0], 0, e->lat_elems() * e->esize, e->stream));
+    CU(cudaMemsetAsync(e->lat[1], 0, e->lat_elems() * e->esize, e->stream));
+    T *lat = (T *)e->lat[0];
+    if ((rc = upload_planes<T>(e, in->f, 9, col0, ncw, lat, Hp, (size_t)NPOP * Hp))) return rc;
+    if ((rc = upload_planes<T>(e, in->g, 9, col0, ncw, lat + 9 * Hp, Hp, (size_t)NPOP * Hp))) return rc;
+    if ((rc = upload_planes<T>(e, in->psi, 1, col0, ncw, (T *)e->psi[0], 0, Hp))) return rc;
+    T *fb = (T *)e->fields;
+    const double *srcs[9] = {in->rho, in->ux, in->uy, in->p, in->mu, in->mix_tau, in->nabla_psix, in->nabla_psiy,
+                             in->nabla_psi2};
+    for (int k = 0; k < 9; ++k) {
+        if (!srcs[k]) continue;  // nabla_psi2 is optional on input (recomputed from psi)
+        if ((rc = upload_planes<T>(e, srcs[k], 1, col0, ncw, fb + k * n, 0, Hp))) return rc;
+    }
+    e->state = ST_PRE;
+    e->iters = 0;
+    return 0;
+}
+
+template <typename T>
+int get_state_t(fdlbm_engine *e, int col0, int ncw, const fdlbm_fields *out)
+{
+    const size_t Hp = e->Hp, n = e->plane_elems();
+    int rc = ensure_fields(e);
+    if (rc) return rc;
+    const T *lat, *psi;
+    if (e->state == ST_PRE) {
+        lat = (const T *)e->lat[e->cur];
+        psi = (const T *)e->psi[e->pcur];
+    } else {
+        if ((rc = launch_step<T>(e, true))) return rc;  // writes lat[1-cur], psi[1-pcur], fields; no swap
+        lat = (const T *)e->lat[1 - e->cur];
+        psi = (const T *)e->psi[1 - e->pcur];
+    }
+    if ((rc = download_planes<T>(e, out->f, 9, col0, ncw, lat, Hp, (size_t)NPOP * Hp))) return rc;
+    if ((rc = download_planes<T>(e, out->g, 9, col0, ncw, lat + 9 * Hp, Hp, (size_t)NPOP * Hp))) return rc;
+    if ((rc = download_planes<T>(e, out->psi, 1, col0, ncw, psi, 0, Hp))) return rc;
+    const T *fb = (const T *)e->fields;
+    double *dsts[9] = {out->rho, out->ux, out->uy, out->p, out->mu, out->mix_tau, out->nabla_psix, out->nabla_psiy,
+                       out->nabla_psi2};
+    for (int k = 0; k < 9; ++k)
+        if ((rc = download_planes<T>(e, dsts[k], 1, col0, ncw, fb + k * n, 0, Hp))) return rc;
+    return 0;
+}
+
+int upload_profile(fdlbm_engine *e, const double *host, void **dev)
+{
+    const int H = e->cfg.H;
+    CU(cudaMalloc(dev, (size_t)e->Hp * e->esize));
+    if (e->cfg.dtype == FDLBM_F64) {
+        CU(cudaMemcpy(*dev, host, (size_t)H * sizeof(double), cudaMemcpyHostToDevice));
+    } else {
+        std::vector<float> tmp(host, host + H);
+        CU(cudaMemcpy(*dev, tmp.data(), (size_t)H * sizeof(float), cudaMemcpyHostToDevice));
+    }
+    return 0;
+}
+
+}  // namespace
+
+extern "C" {
+
+int fdlbm_abi_version(void) { return FDLBM_ABI_VERSION; }
+const char *fdlbm_last_error(void) { return g_err.c_str(); }
+
+int fdlbm_device_count(void)
+{
+    int n = 0;
+    cudaError_t err = cudaGetDeviceCount(&n);
+    if (err != cudaSuccess) return fail(FDLBM_E_CUDA, "cudaGetDeviceCount: %s", cudaGetErrorString(err));
+    return n;
+}
+
+int fdlbm_create(const fdlbm_config *cfg, fdlbm_engine **out)
+{
+    if (!cfg || !out) return fail(FDLBM_E_ARG, "null argument");
+    *out = nullptr;
+    if (cfg->H < 4 || cfg->W < 4) return fail(FDLBM_E_ARG, "grid too small: H=%d W=%d (need >= 4)", cfg->H, cfg->W);
+    if (cfg->dtype != FDLBM_F64 && cfg->dtype != FDLBM_F32) return fail(FDLBM_E_ARG, "bad dtype %d", cfg->dtype);
+    if (cfg->x0 < 0 || cfg->x1 > cfg->W || cfg->x1 - cfg->x0 < 2)
+        return fail(FDLBM_E_ARG, "bad slab [%d,%d) of W=%d (need >= 2 columns)", cfg->x0, cfg->x1, cfg->W);
+    if (cfg->zou_he != FDLBM_ZH_NONE && cfg->x_periodic)
+        return fail(FDLBM_E_ARG, "Zou-He faces and x-periodic wrap are mutually exclusive");
+    if (cfg->zou_he == FDLBM_ZH_NONE && !cfg->x_periodic)
+        return fail(FDLBM_E_ARG, "x faces need either Zou-He (FP/FG) or x_periodic (validation)");
+    if (cfg->zou_he != FDLBM_ZH_NONE && (!cfg->inlet_ux || !cfg->outlet_ux))
+        return fail(FDLBM_E_ARG, "Zou-He faces need inlet_ux and outlet_ux profiles");
+    if (cfg->x_periodic && !cfg->external_halo && (cfg->x0 != 0 || cfg->x1 != cfg->W))
+        return fail(FDLBM_E_ARG, "a slab of an x-periodic grid needs external_halo=1");
+    if (!cfg->x_periodic && !cfg->external_halo && (cfg->x0 != 0 || cfg->x1 != cfg->W))
+        return fail(FDLBM_E_ARG, "a proper slab needs external_halo=1");
+    if (!(cfg->tau > 0)) return fail(FDLBM_E_ARG, "tau must be positive");
+    int ndev = 0;
+    cudaError_t err = cudaGetDeviceCount(&ndev);
+    if (err != cudaSuccess || ndev == 0)
+        return fail(FDLBM_E_CUDA, "no CUDA device (%s); this library has no CPU path",
+                    err != cudaSuccess ? cudaGetErrorString(err) : "device count 0");
+    if (cfg->device < 0 || cfg->device >= ndev) return fail(FDLBM_E_ARG, "bad device %d of %d", cfg->device, ndev);
+    CU(cudaSetDevice(cfg->device));
+
+    fdlbm_engine *e = new fdlbm_engine();
+    e->cfg = *cfg;
+    e->cfg.inlet_ux = e->cfg.outlet_ux = nullptr;  // borrowed pointers are not kept
+    e->Wl = cfg->x1 - cfg->x0;
+    e->Hp = (cfg->H + 31) / 32 * 32;
+    e->ncols = e->Wl + 2 * G;
+    e->esize = cfg->dtype == FDLBM_F64 ? 8 : 4;
+    e->kernel = cfg->kernel == FDLBM_KERNEL_AUTO ? FDLBM_KERNEL_FUSED : cfg->kernel;
+#define CUE(call)                                                                                     \
+    do {                                                                                              \
+        cudaError_t _e = (call);                                                                      \
+        if (_e != cudaSuccess) {                                                                      \
+            fail(_e == cudaErrorMemoryAllocation ? FDLBM_E_NOMEM : FDLBM_E_CUDA, "%s failed: %s", #call, \
+                 cudaGetErrorString(_e));                                                             \
+            fdlbm_destroy(e);                                                                         \
+            return _e == cudaErrorMemoryAllocation ? FDLBM_E_NOMEM : FDLBM_E_CUDA;                    \
+        }                                                                                             \
+    } while (0)
+    CUE(cudaStreamCreateWithFlags(&e->stream, cudaStreamNonBlocking));
+    for (int k = 0; k < 2; ++k) {
+        CUE(cudaMalloc(&e->lat[k], e->lat_elems() * e->esize));
+        CUE(cudaMemsetAsync(e->lat[k], 0, e->lat_elems() * e->esize, e->stream));
+        CUE(cudaMalloc(&e->psi[k], e->plane_elems() * e->esize));
+        CUE(cudaMemsetAsync(e->psi[k], 0, e->plane_elems() * e->esize, e->stream));
+    }
+    CUE(cudaMalloc(&e->reflect, e->plane_elems()));
+    CUE(cudaMemsetAsync(e->reflect, 0, e->plane_elems(), e->stream));
+    CUE(cudaMalloc(&e->solid_bytes, e->plane_elems()));
+    CUE(cudaMemsetAsync(e->solid_bytes, 0, e->plane_elems(), e->stream));
+    CUE(cudaMalloc(&e->solid, e->plane_elems() / 8));
+    CUE(cudaMemsetAsync(e->solid, 0, e->plane_elems() / 8, e->stream));
+#undef CUE
+    if (cfg->zou_he != FDLBM_ZH_NONE) {
+        int rc = upload_profile(e, cfg->inlet_ux, &e->inlet);
+        if (!rc) rc = upload_profile(e, cfg->outlet_ux, &e->outlet);
+        if (rc) {
+            fdlbm_destroy(e);
+            return rc;
+        }
+    }
+    cudaError_t se = cudaStreamSynchronize(e->stream);
+    if (se != cudaSuccess) {
+        fdlbm_destroy(e);
+        return fail(FDLBM_E_CUDA, "stream sync failed: %s", cudaGetErrorString(se));
+    }
+    *out = e;
+    return 0;
+}
+
+void fdlbm_destroy(fdlbm_engine *e)
+{
+    if (!e) return;
+    cudaSetDevice(e->cfg.device);
+    if (e->stream) cudaStreamSynchronize(e->stream);
+    void *ptrs[] = {e->lat[0], e->lat[1], e->psi[0], e->psi[1], e->fields, e->reflect, e->solid_bytes,
+                    e->solid, e->inlet, e->outlet, e->staging};
+    for (void *p : ptrs)
+        if (p) cudaFree(p);
+    if (e->stream) cudaStreamDestroy(e->stream);
+    delete e;
+}
+
+int fdlbm_set_geometry(fdlbm_engine *e, int col0, int ncols, const uint8_t *solid, const uint8_t *reflect)
+{
+    if (!e || !solid || !reflect) return fail(FDLBM_E_ARG, "null argument");
+    if (ncols <= 0 || col0 < 0 || col0 + ncols > e->cfg.W) return fail(FDLBM_E_ARG, "bad column window");
+    CU(cudaSetDevice(e->cfg.device));
+    const int H = e->cfg.H;
+    const size_t bytes = (size_t)H * ncols;
+    int rc = ensure_staging(e, 2 * bytes);
+    if (rc) return rc;
+    uint8_t *st = (uint8_t *)e->staging;
+    CU(cudaMemcpyAsync(st, solid, bytes, cudaMemcpyHostToDevice, e->stream));
+    CU(cudaMemcpyAsync(st + bytes, reflect, bytes, cudaMemcpyHostToDevice, e->stream));
+    CU(cudaMemsetAsync(e->solid_bytes, 0, e->plane_elems(), e->stream));
+    CU(cudaMemsetAsync(e->reflect, 0, e->plane_elems(), e->stream));
+    // all local columns including the ghosts (their flags drive psi on the one-cell ring)
+    dim3 grid((e->ncols + 31) / 32, (H + 31) / 32), block(32, 8);
+    k_transpose_in<uint8_t, uint8_t><<<grid, block, 0, e->stream>>>(st, H, ncols, col0, e->solid_bytes, (size_t)e->Hp, -G,
+                                                                     e->Wl + G, e->cfg.x0, e->cfg.W, e->cfg.x_periodic);
+    k_transpose_in<uint8_t, uint8_t><<<grid, block, 0, e->stream>>>(st + bytes, H, ncols, col0, e->reflect, (size_t)e->Hp,
+                                                                     -G, e->Wl + G, e->cfg.x0, e->cfg.W, e->cfg.x_periodic);
+    const size_t n = e->plane_elems();
+    k_pack_solid<<<(unsigned)((n + 255) / 256), 256, 0, e->stream>>>(e->solid_bytes, e->solid, n);
+    e->launches += 3;
+    CU(cudaGetLastError());
+    CU(cudaStreamSynchronize(e->stream));
+    e->have_geometry = true;
+    return 0;
+}
+
+int fdlbm_set_state(fdlbm_engine *e, int col0, int ncols, const fdlbm_fields *in)
+{
+    if (!e || !in) return fail(FDLBM_E_ARG, "null argument");
+    if (!in->f || !in->g || !in->psi || !in->rho || !in->ux || !in->uy || !in->p || !in->mu || !in->mix_tau ||
+        !in->nabla_psix || !in->nabla_psiy)
+        return fail(FDLBM_E_ARG, "set_state needs f, g, psi, rho, ux, uy, p, mu, mix_tau, nabla_psix, nabla_psiy");
+    if (ncols <= 0 || col0 < 0 || col0 + ncols > e->cfg.W) return fail(FDLBM_E_ARG, "bad column window");
+    if (!e->have_geometry) return fail(FDLBM_E_STATE, "set_geometry must be called before set_state");
+    CU(cudaSetDevice(e->cfg.device));
+    return e->cfg.dtype == FDLBM_F64 ? set_state_t<double>(e, col0, ncols, in) : set_state_t<float>(e, col0, ncols, in);
+}
+
+int fdlbm_step(fdlbm_engine *e, int n)
+{
+    if (!e) return fail(FDLBM_E_ARG, "null engine");
+    if (n < 0) return fail(FDLBM_E_ARG, "negative step count");
+    if (e->state == ST_EMPTY) return fail(FDLBM_E_STATE, "set_state must be called before step");
+    if (e->cfg.external_halo && n > 1)
+        return fail(FDLBM_E_ARG, "external_halo engines advance one step per call (halo exchange in between)");
+    CU(cudaSetDevice(e->cfg.device));
+    return e->cfg.dtype == FDLBM_F64 ? do_steps<double>(e, n) : do_steps<float>(e, n);
+}
+
+int fdlbm_get_state(fdlbm_engine *e, int col0, int ncols, const fdlbm_fields *out)
+{
+    if (!e || !out) return fail(FDLBM_E_ARG, "null argument");
+    if (e->state == ST_EMPTY) return fail(FDLBM_E_STATE, "no state loaded");
+    if (ncols <= 0 || col0 < 0 || col0 + ncols > e->cfg.W) return fail(FDLBM_E_ARG, "bad column window");
+    CU(cudaSetDevice(e->cfg.device));
+    return e->cfg.dtype == FDLBM_F64 ? get_state_t<double>(e, col0, ncols, out) : get_state_t<float>(e, col0, ncols, out);
+}
+
+int64_t fdlbm_iterations(const fdlbm_engine *e) { return e ? e->iters : -1; }
+
+int fdlbm_sync(fdlbm_engine *e)
+{
+    if (!e) return fail(FDLBM_E_ARG, "null engine");
+    CU(cudaSetDevice(e->cfg.device));
+    CU(cudaStreamSynchronize(e->stream));
+    return 0;
+}
+
+void *fdlbm_stream(fdlbm_engine *e) { return e ? (void *)e->stream : nullptr; }
+int64_t fdlbm_launch_count(const fdlbm_engine *e) { return e ? e->launches : -1; }
+
+int fdlbm_halo_regions(fdlbm_engine *e, fdlbm_halo *out)
+{
+    if (!e || !out) return fail(FDLBM_E_ARG, "null argument");
+    const size_t col = (size_t)NPOP * e->Hp * e->esize;
+    char *b = (char *)e->lat[e->cur];
+    out->recv_lo = b;
+    out->send_lo = b + (size_t)G * col;
+    out->send_hi = b + (size_t)e->Wl * col;
+    out->recv_hi = b + (size_t)(e->Wl + G) * col;
+    out->bytes = (size_t)G * col;
+    return 0;
+}
+
+void *fdlbm_pinned_alloc(size_t bytes)
+{
+    void *p = nullptr;
+    if (cudaHostAlloc(&p, bytes, cudaHostAllocDefault) != cudaSuccess) {
+        fail(FDLBM_E_NOMEM, "cudaHostAlloc(%zu) failed", bytes);
+        return nullptr;
+    }
+    return p;
+}
+
+void fdlbm_pinned_free(void *p)
+{
+    if (p) cudaFreeHost(p);
+}
+
+}  // extern "C"
+
+#include "lbm_ops.cuh"

@@ -1,0 +1,317 @@
+// lbm_ops.cuh -- stateless NumPy-in/NumPy-out operators (included at the end of fdlbm.cu).
+// Each op builds a throw-away engine (device layout, same device functions as the step kernels),
+// runs one small kernel and copies the result back.  They exist so that the reference's module-level
+// functions (stream, Bounce_back.*, Compute.getNabla_* ...) stay callable one by one; a whole run should
+// use fdlbm_step, which keeps the state resident.
+
+namespace fdlbm {
+
+// f,g of every cell <- pull-streamed neighbours (no boundary rule): stream(), fingering_periodic.py:327-343
+template <typename T>
+__global__ void __launch_bounds__(TPB) k_op_stream(const __grid_constant__ LbmParams<T> P)
+{
+    const int y = blockIdx.x * TPB + threadIdx.x, xl = blockIdx.y;
+    if (y >= P.H) return;
+    T f[9], g[9];
+    pull(P, xl, y, 0, 0u, f);
+    pull(P, xl, y, 9, 0u, g);
+    store_cell(P, xl, y, f, g);
+}
+
+// dst (already streamed populations) <- src_opp (pre-stream copy) where the reflect bit is set
+template <typename T>
+__global__ void __launch_bounds__(TPB) k_op_bounce_back(const __grid_constant__ LbmParams<T> P)
+{
+    const int y = blockIdx.x * TPB + threadIdx.x, xl = blockIdx.y;
+    if (y >= P.H) return;
+    const unsigned bits = P.reflect[cell_idx(P.Hp, xl, y)];
+    if (!bits) return;
+    const T *s = P.src + lat_idx(P.Hp, xl, 0, y);
+    T *d = P.dst + lat_idx(P.Hp, xl, 0, y);
+#pragma unroll
+    for (int i = 1; i < 9; ++i)
+        if ((bits >> (i - 1)) & 1u) {
+            d[(size_t)i * P.Hp] = s[(size_t)opp(i) * P.Hp];
+            d[(size_t)(9 + i) * P.Hp] = s[(size_t)(9 + opp(i)) * P.Hp];
+        }
+}
+
+template <typename T>
+__global__ void __launch_bounds__(TPB) k_op_stencils(const __grid_constant__ LbmParams<T> P, FieldPtrs<T> out)
+{
+    const int y = blockIdx.x * TPB + threadIdx.x, xl = blockIdx.y;
+    if (y >= P.H) return;
+    const size_t c = cell_idx(P.Hp, xl, y);
+    stencil_from_array(P, P.psi_old, xl, y, out.gx[c], out.gy[c], out.lap[c]);
+}
+
+// in-place populations of the inlet column's other rows (no streaming): used by the Zou-He operator
+template <typename T>
+struct LocalRow {
+    __device__ __noinline__ T operator()(const LbmParams<T> &P, int xl, int y) const
+    {
+        T f[9];
+        const T *s = P.dst + lat_idx(P.Hp, xl, 0, y);
+#pragma unroll
+        for (int i = 0; i < 9; ++i) f[i] = s[(size_t)i * P.Hp];
+        T psx, psy, lp;
+        stencil_from_array(P, P.psi_old, xl, y, psx, psy, lp);
+        const T mu = chem_potential(P, P.psi_old[cell_idx(P.Hp, xl, y)], lp);
+        return inlet_rho(f, P.inlet_ux[y], psx, mu);
+    }
+};
+
+// zou_he_boundary_inlet/outlet applied in place on the face columns of P.dst
+template <typename T>
+__global__ void __launch_bounds__(TPB) k_op_zou_he(const __grid_constant__ LbmParams<T> P)
+{
+    const int y = blockIdx.x * TPB + threadIdx.x;
+    const int xl = blockIdx.y == 0 ? 0 : P.Wl - 1;
+    if (y >= P.H) return;
+    const int gx = P.gx0 + xl;
+    T f[9], g[9];
+    T *s = P.dst + lat_idx(P.Hp, xl, 0, y);
+#pragma unroll
+    for (int i = 0; i < 9; ++i) {
+        f[i] = s[(size_t)i * P.Hp];
+        g[i] = s[(size_t)(9 + i) * P.Hp];
+    }
+    zou_he_g(P, gx, y, g);
+    zou_he_f(P, xl, gx, y, f, LocalRow<T>());
+    // the corner nodes read rho_inlet of rows 1 / H-2 computed from PRE-update populations
+    // (fingering.py:303-304 evaluates rho_inlet before any assignment); rows 1 and H-2 only rewrite
+    // f1,f5,f8, which inlet_rho does not read, so the in-place read is race-free.
+    store_cell(P, xl, y, f, g);
+}
+
+template <typename T>
+__global__ void __launch_bounds__(TPB) k_op_psi_local(const __grid_constant__ LbmParams<T> P)
+{
+    const int y = blockIdx.x * TPB + threadIdx.x, xl = blockIdx.y;
+    if (y >= P.H) return;
+    T s = P.psi_wall;
+    if (!is_solid(P, xl, y)) {
+        const T *g = P.src + lat_idx(P.Hp, xl, 9, y);
+        s = (((g[0] + g[(size_t)P.Hp]) + (g[(size_t)2 * P.Hp] + g[(size_t)3 * P.Hp])) +
+             ((g[(size_t)4 * P.Hp] + g[(size_t)5 * P.Hp]) + (g[(size_t)6 * P.Hp] + g[(size_t)7 * P.Hp]))) +
+            g[(size_t)8 * P.Hp];
+    }
+    P.psi_new[cell_idx(P.Hp, xl, y)] = s;
+}
+
+template <typename T>
+__global__ void __launch_bounds__(TPB) k_op_moments_local(const __grid_constant__ LbmParams<T> P, FieldPtrs<T> out)
+{
+    const int y = blockIdx.x * TPB + threadIdx.x, xl = blockIdx.y;
+    if (y >= P.H) return;
+    const size_t c = cell_idx(P.Hp, xl, y);
+    T gx, gy, lap;
+    stencil_from_array(P, P.psi_new, xl, y, gx, gy, lap);
+    out.gx[c] = gx;
+    out.gy[c] = gy;
+    out.lap[c] = lap;
+    if (is_solid(P, xl, y)) {
+        out.rho[c] = out.ux[c] = out.uy[c] = out.p[c] = out.mu[c] = out.mix_tau[c] = T(0);
+        return;
+    }
+    T f[9];
+    const T *s = P.src + lat_idx(P.Hp, xl, 0, y);
+#pragma unroll
+    for (int i = 0; i < 9; ++i) f[i] = s[(size_t)i * P.Hp];
+    const T psi = P.psi_new[c];
+    Macro<T> m;
+    moments(P, f, psi, gx, gy, lap, m);
+    out.rho[c] = m.rho;
+    out.ux[c] = m.ux;
+    out.uy[c] = m.uy;
+    out.p[c] = m.p;
+    out.mu[c] = m.mu;
+    const T D = (T(1) - psi) + P.M * (T(1) + psi);
+    out.mix_tau[c] = P.eta6m / (m.rho * D) + T(0.5);
+}
+
+}  // namespace fdlbm
+
+namespace {
+
+struct TempEngine {
+    fdlbm_engine *e = nullptr;
+    ~TempEngine() { fdlbm_destroy(e); }
+};
+
+// whole-grid single-slab f64 engine for an operator call
+int op_engine(TempEngine &t, const fdlbm_config *cfg_in, int H, int W, bool force_periodic)
+{
+    fdlbm_config c;
+    if (cfg_in) {
+        c = *cfg_in;
+    } else {
+        memset(&c, 0, sizeof c);
+        c.H = H;
+        c.W = W;
+        c.tau = 1.0;
+    }
+    c.dtype = FDLBM_F64;
+    c.x0 = 0;
+    c.x1 = c.W;
+    c.external_halo = 0;
+    c.kernel = FDLBM_KERNEL_TWOPASS;
+    if (force_periodic) {
+        c.x_periodic = 1;
+        c.zou_he = FDLBM_ZH_NONE;
+    }
+    int rc = fdlbm_create(&c, &t.e);
+    return rc;
+}
+
+int upload_pops(fdlbm_engine *e, int which, const double *f, const double *g)
+{
+    double *lat = (double *)e->lat[which];
+    const size_t Hp = e->Hp;
+    int rc = upload_planes<double>(e, f, 9, 0, e->cfg.W, lat, Hp, (size_t)NPOP * Hp);
+    if (rc) return rc;
+    return upload_planes<double>(e, g, 9, 0, e->cfg.W, lat + 9 * Hp, Hp, (size_t)NPOP * Hp);
+}
+
+int download_pops(fdlbm_engine *e, int which, double *f, double *g)
+{
+    const double *lat = (const double *)e->lat[which];
+    const size_t Hp = e->Hp;
+    int rc = download_planes<double>(e, f, 9, 0, e->cfg.W, lat, Hp, (size_t)NPOP * Hp);
+    if (rc) return rc;
+    return download_planes<double>(e, g, 9, 0, e->cfg.W, lat + 9 * Hp, Hp, (size_t)NPOP * Hp);
+}
+
+int upload_solid(fdlbm_engine *e, const uint8_t *solid)
+{
+    std::vector<uint8_t> zeros((size_t)e->cfg.H * e->cfg.W, 0);
+    return fdlbm_set_geometry(e, 0, e->cfg.W, solid ? solid : zeros.data(), zeros.data());
+}
+
+}  // namespace
+
+extern "C" {
+
+int fdlbm_op_stream(int H, int W, double *f, double *g)
+{
+    if (!f || !g) return fail(FDLBM_E_ARG, "null argument");
+    TempEngine t;
+    int rc = op_engine(t, nullptr, H, W, true);
+    if (rc) return rc;
+    fdlbm_engine *e = t.e;
+    if ((rc = upload_solid(e, nullptr))) return rc;
+    if ((rc = upload_pops(e, 0, f, g))) return rc;
+    if ((rc = wrap_ghosts(e, e->lat[0]))) return rc;
+    LbmParams<double> P = make_params<double>(e, 0, 0);
+    k_op_stream<double><<<cell_grid(e, e->Wl), TPB, 0, e->stream>>>(P);
+    CU(cudaGetLastError());
+    return download_pops(e, 1, f, g);
+}
+
+int fdlbm_op_bounce_back(int H, int W, const uint8_t *reflect, const double *f_behind, const double *g_behind,
+                         double *f, double *g)
+{
+    if (!reflect || !f_behind || !g_behind || !f || !g) return fail(FDLBM_E_ARG, "null argument");
+    TempEngine t;
+    int rc = op_engine(t, nullptr, H, W, true);
+    if (rc) return rc;
+    fdlbm_engine *e = t.e;
+    std::vector<uint8_t> zeros((size_t)H * W, 0);
+    if ((rc = fdlbm_set_geometry(e, 0, W, zeros.data(), reflect))) return rc;
+    if ((rc = upload_pops(e, 0, f_behind, g_behind))) return rc;
+    if ((rc = upload_pops(e, 1, f, g))) return rc;
+    LbmParams<double> P = make_params<double>(e, 0, 0);
+    k_op_bounce_back<double><<<cell_grid(e, e->Wl), TPB, 0, e->stream>>>(P);
+    CU(cudaGetLastError());
+    return download_pops(e, 1, f, g);
+}
+
+int fdlbm_op_stencils(const fdlbm_config *cfg, const double *psi, double *gx, double *gy, double *lap)
+{
+    if (!cfg || !psi) return fail(FDLBM_E_ARG, "null argument");
+    TempEngine t;
+    int rc = op_engine(t, cfg, 0, 0, false);
+    if (rc) return rc;
+    fdlbm_engine *e = t.e;
+    if ((rc = upload_solid(e, nullptr))) return rc;
+    if ((rc = ensure_fields(e))) return rc;
+    if ((rc = upload_planes<double>(e, psi, 1, 0, e->cfg.W, (double *)e->psi[0], 0, e->Hp))) return rc;
+    if (e->cfg.x_periodic) {  // psi ghost columns wrap
+        const size_t col = (size_t)e->Hp * sizeof(double);
+        char *b = (char *)e->psi[0];
+        CU(cudaMemcpyAsync(b, b + (size_t)e->Wl * col, 2 * col, cudaMemcpyDeviceToDevice, e->stream));
+        CU(cudaMemcpyAsync(b + (size_t)(e->Wl + G) * col, b + (size_t)G * col, 2 * col, cudaMemcpyDeviceToDevice, e->stream));
+    }
+    LbmParams<double> P = make_params<double>(e, 0, 0);
+    FieldPtrs<double> F = field_ptrs<double>(e);
+    k_op_stencils<double><<<cell_grid(e, e->Wl), TPB, 0, e->stream>>>(P, F);
+    CU(cudaGetLastError());
+    if ((rc = download_planes<double>(e, gx, 1, 0, e->cfg.W, F.gx, 0, e->Hp))) return rc;
+    if ((rc = download_planes<double>(e, gy, 1, 0, e->cfg.W, F.gy, 0, e->Hp))) return rc;
+    return download_planes<double>(e, lap, 1, 0, e->cfg.W, F.lap, 0, e->Hp);
+}
+
+int fdlbm_op_collide(const fdlbm_config *cfg, const uint8_t *solid, const fdlbm_fields *io)
+{
+    if (!cfg || !io) return fail(FDLBM_E_ARG, "null argument");
+    TempEngine t;
+    int rc = op_engine(t, cfg, 0, 0, false);
+    if (rc) return rc;
+    fdlbm_engine *e = t.e;
+    if ((rc = upload_solid(e, solid))) return rc;
+    if ((rc = fdlbm_set_state(e, 0, e->cfg.W, io))) return rc;
+    LbmParams<double> P = make_params<double>(e, 1, 0);  // dst = lat[0]
+    k_collide_first<double><<<cell_grid(e, e->Wl), TPB, 0, e->stream>>>(P, field_ptrs<double>(e), (const double *)e->psi[0]);
+    CU(cudaGetLastError());
+    return download_pops(e, 0, io->f, io->g);
+}
+
+int fdlbm_op_zou_he(const fdlbm_config *cfg, const fdlbm_fields *io)
+{
+    if (!cfg || !io || !io->f || !io->g || !io->psi) return fail(FDLBM_E_ARG, "null argument");
+    if (cfg->zou_he == FDLBM_ZH_NONE) return fail(FDLBM_E_ARG, "config has no Zou-He faces");
+    TempEngine t;
+    int rc = op_engine(t, cfg, 0, 0, false);
+    if (rc) return rc;
+    fdlbm_engine *e = t.e;
+    if ((rc = upload_solid(e, nullptr))) return rc;
+    if ((rc = upload_pops(e, 1, io->f, io->g))) return rc;
+    if ((rc = upload_planes<double>(e, io->psi, 1, 0, e->cfg.W, (double *)e->psi[0], 0, e->Hp))) return rc;
+    LbmParams<double> P = make_params<double>(e, 0, 0);  // dst = lat[1], psi_old = psi[0]
+    k_op_zou_he<double><<<cell_grid(e, 2), TPB, 0, e->stream>>>(P);
+    CU(cudaGetLastError());
+    return download_pops(e, 1, io->f, io->g);
+}
+
+int fdlbm_op_moments(const fdlbm_config *cfg, const uint8_t *solid, const fdlbm_fields *io)
+{
+    if (!cfg || !io || !io->f || !io->g) return fail(FDLBM_E_ARG, "null argument");
+    TempEngine t;
+    int rc = op_engine(t, cfg, 0, 0, false);
+    if (rc) return rc;
+    fdlbm_engine *e = t.e;
+    if ((rc = upload_solid(e, solid))) return rc;
+    if ((rc = ensure_fields(e))) return rc;
+    if ((rc = upload_pops(e, 0, io->f, io->g))) return rc;
+    LbmParams<double> P = make_params<double>(e, 0, 0);  // psi_new = psi[1]
+    k_op_psi_local<double><<<cell_grid(e, e->Wl), TPB, 0, e->stream>>>(P);
+    if (e->cfg.x_periodic) {
+        const size_t col = (size_t)e->Hp * sizeof(double);
+        char *b = (char *)e->psi[1];
+        CU(cudaMemcpyAsync(b, b + (size_t)e->Wl * col, 2 * col, cudaMemcpyDeviceToDevice, e->stream));
+        CU(cudaMemcpyAsync(b + (size_t)(e->Wl + G) * col, b + (size_t)G * col, 2 * col, cudaMemcpyDeviceToDevice, e->stream));
+    }
+    FieldPtrs<double> F = field_ptrs<double>(e);
+    k_op_moments_local<double><<<cell_grid(e, e->Wl), TPB, 0, e->stream>>>(P, F);
+    CU(cudaGetLastError());
+    const size_t Hp = e->Hp;
+    const int W = e->cfg.W;
+    if ((rc = download_planes<double>(e, io->psi, 1, 0, W, (const double *)e->psi[1], 0, Hp))) return rc;
+    double *dsts[9] = {io->rho, io->ux, io->uy, io->p, io->mu, io->mix_tau, io->nabla_psix, io->nabla_psiy, io->nabla_psi2};
+    double *srcs[9] = {F.rho, F.ux, F.uy, F.p, F.mu, F.mix_tau, F.gx, F.gy, F.lap};
+    for (int k = 0; k < 9; ++k)
+        if ((rc = download_planes<double>(e, dsts[k], 1, 0, W, srcs[k], 0, Hp))) return rc;
+    return 0;
+}
+
+}  // extern "C"

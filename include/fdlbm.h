@@ -1,0 +1,148 @@
+/*
+ * fdlbm.h -- C ABI of the B200-native two-phase D2Q9 lattice-Boltzmann engine.
+ *
+ * The reference (ebinan92/Fingering_dynamics) has no FFI: its boundary is the Python module surface
+ * of lattice_boltzmann/*.py, and its hot path is the body of `for i in range(MAX_T)` inlined in each
+ * driver's main() (fingering_periodic.py:454-479, fingering.py:558-585, validation.py:392-409).
+ * This header is what a ctypes binding of that path binds instead.  Every entry
+ * point names the reference code it replaces.
+ *
+ * Conventions
+ *   - plain pointers and sizes only; host arrays are borrowed for the duration of the call;
+ *   - host arrays use the REFERENCE layout: C-order float64, populations (9,H,ncols), fields (H,ncols),
+ *     x (axis 1) = flow direction; `col0,ncols` say which global columns the arrays hold
+ *     (col0=0, ncols=W for the whole grid);
+ *   - every function returns 0 on success or a negative FDLBM_E_* code and never throws; the message is
+ *     available from fdlbm_last_error(); there is NO CPU fallback: without a CUDA device
+ *     fdlbm_create fails with FDLBM_E_CUDA;
+ *   - an engine owns its device memory and one CUDA stream; calls on one engine must be serialised by
+ *     the caller, distinct engines are independent.
+ */
+#ifndef FDLBM_H
+#define FDLBM_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define FDLBM_ABI_VERSION 1
+
+enum { FDLBM_OK = 0, FDLBM_E_ARG = -1, FDLBM_E_CUDA = -2, FDLBM_E_STATE = -3, FDLBM_E_NOMEM = -4 };
+enum { FDLBM_F64 = 0, FDLBM_F32 = 1 };
+/* Zou-He flavour of the x faces.
+ * FDLBM_ZH_FP: fingering_periodic.py:268-324 (all rows, per-row velocity profile on both faces);
+ * FDLBM_ZH_FG: fingering.py:298-390 (inlet rows 1..H-2 + the two corner nodes, outlet corner copies). */
+enum { FDLBM_ZH_NONE = 0, FDLBM_ZH_FP = 1, FDLBM_ZH_FG = 2 };
+/* step kernel: FUSED = one pass per step (psi ring recomputed on chip);
+ * TWOPASS = psi staged through HBM, kept as the in-library cross-check of the fused kernel. */
+enum { FDLBM_KERNEL_AUTO = 0, FDLBM_KERNEL_TWOPASS = 1, FDLBM_KERNEL_FUSED = 2 };
+
+typedef struct fdlbm_engine fdlbm_engine;
+
+typedef struct {
+    int32_t H, W;        /* global grid: rows (y) x columns (x)                                        */
+    int32_t dtype;       /* FDLBM_F64 | FDLBM_F32: storage and arithmetic type on the device           */
+    int32_t psi_y_wall;  /* 0: psi stencil wraps in y (fingering_periodic.py:218-225);
+                            1: ghost rows = psi_wall (fingering.py:224, validation.py:246)             */
+    int32_t x_periodic;  /* 0: ghost columns psi_left/psi_right (fingering_periodic.py:94-95,218);
+                            1: everything wraps in x (validation.py)                                   */
+    int32_t zou_he;      /* FDLBM_ZH_*                                                                 */
+    int32_t kernel;      /* FDLBM_KERNEL_*                                                             */
+    int32_t device;      /* CUDA device ordinal                                                        */
+    int32_t x0, x1;      /* slab: global columns [x0,x1) owned by this engine (0,W = whole grid)       */
+    int32_t external_halo; /* 1: the caller fills the 2 ghost columns per side before every step
+                              (multi-GPU slabs, see fdlbm_halo_regions); 0: the engine wraps locally   */
+    double tau;          /* relaxation time of g (fingering_periodic.py:26,263)                        */
+    double gamma;        /* mobility (fingering_periodic.py:40,164,168)                                */
+    double a, kappa;     /* mu = a psi (1-psi^2) - kappa lap psi (fingering_periodic.py:141-144);
+                            validation.py's a psi (psi^2-1) with a>0 is the same with -a               */
+    double Eta_n, M;     /* viscosities of tau_mix (fingering_periodic.py:201-208)                     */
+    double psi_wall;     /* wettability: psi of solid cells and ghost rows (fingering_periodic.py:93,212) */
+    double psi_left, psi_right; /* psi ghost columns and Zou-He targets (+1 / -1)                      */
+    double outlet_f3_coef;      /* 2/3 (fingering_periodic.py:317) or 1.5 (fingering.py:378)           */
+    const double *inlet_ux;     /* H per-row face velocities (fingering_periodic.py:270-271), or NULL  */
+    const double *outlet_ux;    /* H values (fingering_periodic.py:306-307), or NULL                   */
+} fdlbm_config;
+
+/* Host-side view of the macroscopic state the reference's Compute object holds
+ * (fingering_periodic.py:98-113).  "Masked" 1-D reference arrays are passed as full (H,ncols) grids;
+ * entries at solid cells are ignored on input and zero on output.  Any pointer may be NULL on output. */
+typedef struct {
+    double *f, *g;                          /* (9,H,ncols) */
+    double *psi, *rho, *ux, *uy, *p, *mu, *mix_tau;
+    double *nabla_psix, *nabla_psiy, *nabla_psi2;
+} fdlbm_fields;
+
+int fdlbm_abi_version(void);
+/* message of the last failing call on this thread (also valid when fdlbm_create failed) */
+const char *fdlbm_last_error(void);
+/* number of CUDA devices visible, or FDLBM_E_CUDA */
+int fdlbm_device_count(void);
+
+/* Replaces Createblock + Bounce_back + Compute construction as the owner of the run's state. */
+int fdlbm_create(const fdlbm_config *cfg, fdlbm_engine **out);
+void fdlbm_destroy(fdlbm_engine *e);
+
+/* Geometry.  solid: 1 = block cell (block_psi_all == 1, fingering_periodic.py:450-451).
+ * reflect: bit (i-1) set <=> after streaming, f_i and g_i of this cell are replaced by the pre-stream
+ * f_opp(i), g_opp(i) of the SAME cell -- the union of the class tables of bounce_back.py:89-167 /
+ * 25-86 and of the wall rows (fingering.py:573, validation.py:357-376).  Both (H,ncols) uint8. */
+int fdlbm_set_geometry(fdlbm_engine *e, int col0, int ncols, const uint8_t *solid, const uint8_t *reflect);
+
+/* Load the state a reference iteration starts from: populations f,g plus the macroscopic arrays the
+ * FIRST collision reads (rho, ux, uy, p, mu, mix_tau, psi, nabla_psix, nabla_psiy) exactly as the
+ * caller holds them -- Compute.__init__ leaves them mutually inconsistent (fingering_periodic.py:111,
+ * fingering.py:121-123) and parity needs that.  Resets the step counter. */
+int fdlbm_set_state(fdlbm_engine *e, int col0, int ncols, const fdlbm_fields *in);
+
+/* Advance n reference iterations (fingering_periodic.py:455-479).  Asynchronous on the engine stream. */
+int fdlbm_step(fdlbm_engine *e, int n);
+
+/* Read back what the reference holds after the iterations done so far: pre-collision f, g and all
+ * macroscopic fields (fingering_periodic.py:470-479).  Does not disturb the run. */
+int fdlbm_get_state(fdlbm_engine *e, int col0, int ncols, const fdlbm_fields *out);
+
+/* iterations completed since fdlbm_set_state */
+int64_t fdlbm_iterations(const fdlbm_engine *e);
+/* block until everything queued on the engine stream is done */
+int fdlbm_sync(fdlbm_engine *e);
+/* the engine's cudaStream_t (for CUDA-event timing on the launching stream) */
+void *fdlbm_stream(fdlbm_engine *e);
+/* kernels launched by this engine since creation (bench.py's gpu_launches) */
+int64_t fdlbm_launch_count(const fdlbm_engine *e);
+
+/* Multi-GPU slabs (no counterpart in the reference, which is single-process).  Device pointers into
+ * the lattice holding the current state: per side, `bytes` contiguous bytes to send (the 2 owned
+ * edge columns) and to receive into (the 2 ghost columns).  Valid until the next fdlbm_step. */
+typedef struct {
+    void *send_lo, *recv_lo, *send_hi, *recv_hi;
+    size_t bytes;
+} fdlbm_halo;
+int fdlbm_halo_regions(fdlbm_engine *e, fdlbm_halo *out);
+
+/* page-locked host memory for the e2e path */
+void *fdlbm_pinned_alloc(size_t bytes);
+void fdlbm_pinned_free(void *p);
+
+/* ---- stateless operators: NumPy-in / NumPy-out twins of the reference's module functions -------- */
+/* stream(f, g), fingering_periodic.py:327-343 (in place, all cells, wrap on both axes) */
+int fdlbm_op_stream(int H, int W, double *f, double *g);
+/* Bounce_back.halfway_bounceback_* / bottom_top_wall with the classes already folded into reflect bits */
+int fdlbm_op_bounce_back(int H, int W, const uint8_t *reflect, const double *f_behind, const double *g_behind,
+                         double *f, double *g);
+/* Compute.getNabla_psix/psiy/psi2 (fingering_periodic.py:214-256 and twins); outputs may be NULL */
+int fdlbm_op_stencils(const fdlbm_config *cfg, const double *psi, double *gx, double *gy, double *lap);
+/* the collision of one iteration on fluid cells (fingering_periodic.py:455-460), in place on f, g */
+int fdlbm_op_collide(const fdlbm_config *cfg, const uint8_t *solid, const fdlbm_fields *io);
+/* zou_he_boundary_inlet + _outlet (fingering_periodic.py:268-324 / fingering.py:298-390), in place */
+int fdlbm_op_zou_he(const fdlbm_config *cfg, const fdlbm_fields *io);
+/* the moment updates of one iteration (fingering_periodic.py:470-479): f,g in; all fields out */
+int fdlbm_op_moments(const fdlbm_config *cfg, const uint8_t *solid, const fdlbm_fields *io);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* FDLBM_H */

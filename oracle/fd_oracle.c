@@ -217,6 +217,12 @@ EXPORT void fdo_stream(int H, int W, double *f, double *g)
 
 static const int OPP[9] = {0, 3, 4, 1, 2, 7, 8, 5, 6};
 
+static void par_copy(double *dst, const double *src, size_t n)
+{
+#pragma omp parallel for schedule(static)
+    for (long k = 0; k < (long)n; ++k) dst[k] = src[k];
+}
+
 static inline void reflect(int H, int W, const double *fb, const double *gb, double *f, double *g, int i,
                            int y, int x)
 {
@@ -247,6 +253,7 @@ EXPORT void fdo_bb_circle(int H, int W, const uint8_t *masks, const double *fb, 
     };
     for (int k = 0; k < 12; ++k) {
         const uint8_t *m = masks + (size_t)k * H * W;
+#pragma omp parallel for schedule(static)
         for (int y = 0; y < H; ++y)
             for (int x = 0; x < W; ++x)
                 if (m[IDX(y, x)])
@@ -289,6 +296,7 @@ EXPORT void fdo_bb_rect(int H, int W, const int *corners, int n, const double *f
         {8, -1, -1}, /* se corner BB:81 */
     };
     for (int k = 0; k < 8; ++k)
+#pragma omp parallel for schedule(static)
         for (int y = 0; y < H; ++y)
             for (int x = 0; x < W; ++x)
                 if (CLS(k, y, x))
@@ -485,8 +493,8 @@ EXPORT void fdo_iterate(const fdo_params *P, const fdo_geom *G, fdo_state *S, in
     double *fb = (double *)malloc(sizeof(double) * np), *gb = (double *)malloc(sizeof(double) * np);
     for (int it = 0; it < n_iter; ++it) {
         fdo_collide(P, G->mask, S->f, S->g, S->rho, S->ux, S->uy, S->p, S->mu, S->mix_tau, S->psi, S->gx, S->gy);
-        memcpy(fb, S->f, sizeof(double) * np);
-        memcpy(gb, S->g, sizeof(double) * np);
+        par_copy(fb, S->f, np);
+        par_copy(gb, S->g, np);
         fdo_stream(H, W, S->f, S->g);
         if (G->circ_masks) fdo_bb_circle(H, W, G->circ_masks, fb, gb, S->f, S->g);
         if (G->rect_corners) fdo_bb_rect(H, W, G->rect_corners, G->n_rects, fb, gb, S->f, S->g);

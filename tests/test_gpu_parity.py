@@ -1,0 +1,194 @@
+"""GPU parity: the CUDA engine (through the C ABI) against the oracle and the golden fixtures.
+
+Tolerance (BASELINE.json north_star): fp64 fields within 1e-10 relative to the field's max-abs.  The
+fixtures come from the unmodified reference, so "engine vs golden" is "engine vs reference".
+fp32: tolerance measured and stated in FP32_TOL below (DESIGN.md "fp32 variant").
+"""
+import numpy as np
+import pytest
+
+from tests import helpers as hp
+
+pytestmark = pytest.mark.gpu
+
+TOL64 = 1e-10
+# fp32 storage + fp32 arithmetic, relative to the field's max-abs after <= 40 steps of the small cases
+FP32_TOL = {"psi": 2e-5, "rho": 2e-5, "ux": 2e-3, "uy": 2e-3}
+
+CHECKPOINTS = ((1, True), (2, True), (10, True), (40, False))
+
+
+def _compare(got, d, tag, names, tol, mask=None):
+    worst = {}
+    for k in names:
+        ref = d["%s_%s" % (tag, k)]
+        g = got[k]
+        if mask is not None and k not in ("f", "g", "psi", "nabla_psix", "nabla_psiy", "nabla_psi2"):
+            g = np.where(mask, g, 0.0)
+        err = hp.rel_err(g, ref)
+        worst[k] = err
+        assert err <= tol, "%s %s: rel err %.3e > %.1e" % (tag, k, err, tol)
+    return worst
+
+
+@pytest.mark.parametrize("kernel", ["twopass", "fused"])
+@pytest.mark.parametrize("name", ["fp_small", "fg_small", "va_small", "va_small_wet"])
+def test_trajectory_matches_reference_fixtures(golden, name, kernel):
+    d = golden(name)
+    mask = d.get("mask")
+    e = hp.ENGINES[name](d, kernel=kernel)
+    e.set_state(**hp.state_for_engine(d, "s0"))
+    done = 0
+    for step, pops in CHECKPOINTS:
+        e.step(step - done)
+        done = step
+        names = [k for k in hp.ALL_FIELDS if "s%d_%s" % (step, k) in d and (pops or k not in ("f", "g"))]
+        got = e.get_state(names)
+        _compare(got, d, "s%d" % step, names, TOL64, mask)
+    assert e.iterations == 40
+    e.close()
+
+
+@pytest.mark.parametrize("name", ["fp_small", "fg_small", "va_small"])
+def test_get_state_before_any_step_returns_the_input(golden, name):
+    d = golden(name)
+    e = hp.ENGINES[name](d)
+    s0 = hp.state_for_engine(d, "s0")
+    e.set_state(**s0)
+    got = e.get_state(("f", "g", "psi", "rho"))
+    for k in ("f", "g", "psi", "rho"):
+        assert np.array_equal(got[k], s0[k]), k
+    e.close()
+
+
+@pytest.mark.parametrize("name", ["fp_small", "fg_small", "va_small"])
+def test_fused_kernel_is_bit_identical_to_twopass(golden, name):
+    d = golden(name)
+    res = {}
+    for kernel in ("twopass", "fused"):
+        e = hp.ENGINES[name](d, kernel=kernel)
+        e.set_state(**hp.state_for_engine(d, "s0"))
+        e.step(25)
+        res[kernel] = e.get_state(("f", "g", "psi", "rho", "ux", "uy"))
+        e.close()
+    for k in res["fused"]:
+        assert np.array_equal(res["fused"][k], res["twopass"][k]), k
+
+
+@pytest.mark.parametrize("name", ["fp_small", "fg_small", "va_small"])
+def test_matches_oracle_run_in_chunks(golden, name):
+    """step(n) in uneven chunks with read-backs in between == oracle iterate, i.e. get_state does not
+    disturb the run and the first-collision / finalize asymmetry is handled."""
+    d = golden(name)
+    run = hp.ORACLES[name](d)
+    e = hp.ENGINES[name](d)
+    e.set_state(**hp.state_for_engine(d, "s0"))
+    mask = d.get("mask")
+    for n in (1, 3, 1, 7, 5):
+        e.step(n)
+        a = run.iterate(n)
+        got = e.get_state(("psi", "rho", "ux", "uy", "f", "g"))
+        for k in got:
+            ref = a[k]
+            g = got[k] if (mask is None or k in ("f", "g", "psi")) else np.where(mask, got[k], 0.0)
+            r = ref if (mask is None or k in ("f", "g", "psi")) else np.where(mask, ref, 0.0)
+            assert hp.rel_err(g, r) <= TOL64, (n, k, hp.rel_err(g, r))
+    e.close()
+
+
+@pytest.mark.parametrize("name", ["fp_small", "fg_small", "va_small"])
+def test_fp32_variant_within_stated_tolerance(golden, name):
+    d = golden(name)
+    mask = d.get("mask")
+    e = hp.ENGINES[name](d, dtype="f32")
+    e.set_state(**hp.state_for_engine(d, "s0"))
+    e.step(40)
+    got = e.get_state(("psi", "rho", "ux", "uy"))
+    for k, tol in FP32_TOL.items():
+        g = got[k] if (mask is None or k == "psi") else np.where(mask, got[k], 0.0)
+        err = hp.rel_err(g, d["s40_" + k])
+        assert err <= tol, "%s fp32 %s rel err %.3e > %.1e" % (name, k, err, tol)
+    # interface position: sign of psi must agree wherever the reference is clearly on one side
+    ref = d["s40_psi"]
+    clear = np.abs(ref) > 1e-3
+    assert np.array_equal(np.sign(got["psi"][clear]), np.sign(ref[clear]))
+    e.close()
+
+
+def _fp_full_inputs(d):
+    from oracle import oracle as orc
+    H, W = int(d["H"]), int(d["W"])
+    mask = np.unpackbits(d["mask_bits"])[:H * W].reshape(H, W).astype(bool)
+    cls = np.unpackbits(d["class_bits"])[:12 * H * W].reshape(12, H, W).astype(bool)
+    P = hp.fp_params(d)
+    s0 = orc.fp_initial_state(P, mask)
+    return H, W, mask, cls, P, s0
+
+
+def test_config1_full_grid_against_oracle_and_reference_scalars(golden):
+    """config 1 as shipped (400x400, 90 circles, fingering_periodic.py:15-40,406-420)."""
+    from oracle import oracle as orc
+    from fingering_dynamics_b200 import Engine, geometry as geo
+    d = golden("fp_full_scalars")
+    H, W, mask, cls, P, s0 = _fp_full_inputs(d)
+    e = Engine(H, W, tau=P.tau, gamma=P.gamma, a=P.a, kappa=P.kappa, Eta_n=P.Eta_n, M=P.M, psi_wall=P.psi_wall,
+               zou_he="fp", inlet_ux=d["inlet_ux"], outlet_ux=d["inlet_ux"])
+    e.set_geometry(~mask, geo.reflect_bits_circle(cls[0:4], cls[4:8], cls[8:12]))
+    e.set_state(f=s0["f"], g=s0["g"], psi=s0["psi"], rho=s0["rho"], ux=s0["ux"], uy=s0["uy"], p=s0["p"], mu=s0["mu"],
+                mix_tau=s0["mix_tau"], nabla_psix=s0["gx"], nabla_psiy=s0["gy"], nabla_psi2=s0["lap"])
+    run = orc.Run(P, s0, mask=mask, circ_masks=cls.astype(np.uint8), zou_he=1, inlet_ux=d["inlet_ux"],
+                  outlet_ux=d["inlet_ux"])
+    done = 0
+    for step in (1, 10, 100):
+        e.step(step - done)
+        a = run.iterate(step - done)
+        done = step
+        got = e.get_state(("psi", "rho", "ux", "uy"))
+        for k in got:
+            ref = a[k] if k == "psi" else np.where(mask, a[k], 0.0)
+            assert hp.rel_err(got[k], ref) <= TOL64, (step, k, hp.rel_err(got[k], ref))
+        # the reference's own numbers (tests/golden/make_golden.py --full)
+        tag = "s%d" % step
+        assert abs(got["psi"].sum() - float(d[tag + "_sum_psi"])) <= 1e-10 * abs(float(d[tag + "_sum_psi"]))
+        assert abs(got["rho"][mask].sum() - float(d[tag + "_sum_rho"])) <= 1e-10 * float(d[tag + "_sum_rho"])
+        assert hp.rel_err(got["psi"][::5, ::5], d[tag + "_psi_sub"]) <= TOL64
+        assert hp.rel_err(got["ux"][::5, ::5], d[tag + "_ux_sub"]) <= TOL64
+    e.step(1000 - done)
+    got = e.get_state(("psi", "rho", "ux", "uy"))
+    assert abs(got["psi"].sum() - float(d["s1000_sum_psi"])) <= 1e-10 * abs(float(d["s1000_sum_psi"]))
+    assert abs(got["rho"][mask].sum() - float(d["s1000_sum_rho"])) <= 1e-10 * float(d["s1000_sum_rho"])
+    for k in ("psi", "rho", "ux", "uy"):
+        assert hp.rel_err(got[k][::5, ::5], d["s1000_%s_sub" % k]) <= TOL64, k
+    e.close()
+
+
+def test_ops_match_reference_fixtures(golden):
+    """stateless operators (NumPy in / NumPy out) against the reference's own outputs."""
+    import ctypes
+    from fingering_dynamics_b200 import _native as nat, geometry as geo
+    d = golden("ops")
+    H, W = int(d["H"]), int(d["W"])
+    L = nat.lib()
+    f, g = d["f_in"].copy(), d["g_in"].copy()
+    nat.check(L.fdlbm_op_stream(H, W, nat.ptr(f), nat.ptr(g)))
+    assert np.array_equal(f, d["f_stream"]) and np.array_equal(g, d["g_stream"])
+
+    bits = geo.reflect_bits_circle([d["circ_side_%d" % k] for k in range(4)],
+                                   [d["circ_concave_%d" % k] for k in range(4)],
+                                   [d["circ_convex_%d" % k] for k in range(4)])
+    f, g = d["f_stream"].copy(), d["g_stream"].copy()
+    nat.check(L.fdlbm_op_bounce_back(H, W, nat.ptr(bits), nat.ptr(d["f_in"]), nat.ptr(d["g_in"]), nat.ptr(f), nat.ptr(g)))
+    assert np.array_equal(f, d["f_bb_circle"]) and np.array_equal(g, d["g_bb_circle"])
+
+    for pre, wall, yw in (("fp", -0.5, 0), ("fg", -0.7, 1)):
+        cfg = nat.Config()
+        cfg.H, cfg.W, cfg.psi_y_wall, cfg.zou_he, cfg.tau = H, W, yw, 1, 1.0
+        cfg.psi_wall, cfg.psi_left, cfg.psi_right = wall, 1.0, -1.0
+        prof = np.zeros(H)
+        cfg.inlet_ux = cfg.outlet_ux = prof.ctypes.data
+        psi = np.ascontiguousarray(np.where(d["stencil_mask"], d["psi_in"], wall))
+        gx, gy, lap = (np.empty((H, W)) for _ in range(3))
+        nat.check(L.fdlbm_op_stencils(ctypes.byref(cfg), nat.ptr(psi), nat.ptr(gx), nat.ptr(gy), nat.ptr(lap)))
+        assert hp.rel_err(gx, d[pre + "_nabla_psix"]) <= 1e-14
+        assert hp.rel_err(gy, d[pre + "_nabla_psiy"]) <= 1e-14
+        assert hp.rel_err(lap, d[pre + "_nabla_psi2"]) <= 1e-14

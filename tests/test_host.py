@@ -1,0 +1,146 @@
+"""CPU-side checks: the C-ABI library builds, loads and exports what include/fdlbm.h declares; it fails
+loudly without a GPU; and the host-side geometry folding (class masks -> reflect bits) agrees with the
+reference's class tables as restated by the oracle."""
+import ctypes
+import os
+import re
+
+import numpy as np
+import pytest
+
+from oracle import oracle as orc
+from tests import helpers as hp
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _header_symbols():
+    txt = open(os.path.join(ROOT, "include", "fdlbm.h")).read()
+    txt = re.sub(r"/\*.*?\*/", "", txt, flags=re.S)
+    return sorted(set(re.findall(r"\b(fdlbm_[a-z0-9_]+)\s*\(", txt)))
+
+
+def test_library_exports_every_declared_symbol():
+    from fingering_dynamics_b200 import _native as nat
+    L = nat.lib()
+    syms = _header_symbols()
+    assert len(syms) >= 20
+    for s in syms:
+        assert hasattr(L, s), "libfdlbm.so does not export " + s
+        assert s in nat._SIGS, "binding missing for " + s
+    assert L.fdlbm_abi_version() == 1
+
+
+def test_no_cpu_fallback_without_a_device():
+    """On a box without CUDA, creating an engine must raise (never silently compute on the CPU)."""
+    from fingering_dynamics_b200 import _native as nat
+    if nat.lib().fdlbm_device_count() > 0:
+        pytest.skip("a CUDA device is present")
+    from fingering_dynamics_b200 import Engine
+    with pytest.raises(nat.FdlbmError) as ei:
+        Engine(16, 16, tau=0.8, gamma=1.0, a=-0.04, kappa=0.09, Eta_n=0.1, M=20.0, psi_wall=0.0, x_periodic=True)
+    assert "CUDA" in str(ei.value) or "device" in str(ei.value)
+    rc = nat.lib().fdlbm_op_stream(8, 8, np.zeros((9, 8, 8)).ctypes.data, np.zeros((9, 8, 8)).ctypes.data)
+    assert rc < 0
+
+
+def test_config_validation_messages():
+    from fingering_dynamics_b200 import _native as nat
+    cfg = nat.Config()
+    h = ctypes.c_void_p()
+    rc = nat.lib().fdlbm_create(ctypes.byref(cfg), ctypes.byref(h))
+    assert rc == -1 and b"grid too small" in nat.lib().fdlbm_last_error()
+    assert nat.lib().fdlbm_step(None, 1) == -1
+    assert nat.lib().fdlbm_iterations(None) == -1
+
+
+def _apply_bits(bits, fb, gb, f, g):
+    opp = [0, 3, 4, 1, 2, 7, 8, 5, 6]
+    for i in range(1, 9):
+        m = (bits >> (i - 1)) & 1 == 1
+        f[i][m] = fb[opp[i]][m]
+        g[i][m] = gb[opp[i]][m]
+
+
+def test_reflect_bits_equal_the_class_tables(golden):
+    """pull + reflect bits == stream + halfway_bounceback_* (bit-identical), for circles, rectangles,
+    wall rows and left_boundary -- against the golden outputs of the reference itself."""
+    from fingering_dynamics_b200 import geometry as geo
+    d = golden("ops")
+    H, W = int(d["H"]), int(d["W"])
+    fb, gb = d["f_in"], d["g_in"]
+
+    bits = geo.reflect_bits_circle([d["circ_side_%d" % k] for k in range(4)],
+                                   [d["circ_concave_%d" % k] for k in range(4)],
+                                   [d["circ_convex_%d" % k] for k in range(4)])
+    f, g = d["f_stream"].copy(), d["g_stream"].copy()
+    _apply_bits(bits, fb, gb, f, g)
+    assert np.array_equal(f, d["f_bb_circle"]) and np.array_equal(g, d["g_bb_circle"])
+
+    bits = geo.reflect_bits_rect(hp.corner_dicts(d["rect_corners"]), H, W)
+    f, g = d["f_stream"].copy(), d["g_stream"].copy()
+    _apply_bits(bits, fb, gb, f, g)
+    assert np.array_equal(f, d["f_bb_rect"]) and np.array_equal(g, d["g_bb_rect"])
+    bits |= geo.reflect_bits_wall_rows(H, W, 1, H - 2)
+    f, g = d["f_stream"].copy(), d["g_stream"].copy()
+    _apply_bits(bits, fb, gb, f, g)
+    assert np.array_equal(f, d["f_bb_rect_walls"]) and np.array_equal(g, d["g_bb_rect_walls"])
+
+    bits = geo.reflect_bits_wall_rows(H, W, 0, H - 1)
+    f, g = d["f_stream"].copy(), d["g_stream"].copy()
+    _apply_bits(bits, fb, gb, f, g)
+    assert np.array_equal(f, d["f_bb_va"]) and np.array_equal(g, d["g_bb_va"])
+
+    bits = geo.reflect_bits_left_boundary(H, W, 3)
+    f, g = d["f_stream"].copy(), d["g_stream"].copy()
+    _apply_bits(bits, fb, gb, f, g)
+    assert np.array_equal(f, d["f_left_boundary"]) and np.array_equal(g, d["g_left_boundary"])
+
+
+def test_solid_flag_ignores_doubly_covered_cells(golden):
+    from fingering_dynamics_b200 import geometry as geo
+    d = golden("geometry")
+    bpa = d["circ_overlap_block_psi_all"]
+    assert bpa.max() == 2
+    s = geo.solid_from_block_psi(bpa)
+    assert s.dtype == np.uint8 and np.array_equal(s == 1, bpa == 1) and s[bpa == 2].sum() == 0
+
+
+def test_synthetic_generator_windows_and_initial_state():
+    """a slab's geometry window equals the same columns of the global geometry, and the product's
+    host-side initial state (synthetic.fp_initial_state) equals the oracle's restatement of
+    Compute.__init__ (fingering_periodic.py:90-121) bit for bit."""
+    from fingering_dynamics_b200 import synthetic as syn
+    from fingering_dynamics_b200.slab import slab_bounds
+    H, W = 160, 400
+    solid, refl = syn.porous_geometry(H, W)
+    assert 0.05 < solid.mean() < 0.3 and refl.any()
+    cover = 0
+    for rank in range(3):
+        x0, x1 = slab_bounds(W, 3, rank)
+        lo, hi = max(0, x0 - 2), min(W, x1 + 2)
+        s, r = syn.porous_geometry(H, W, col0=lo, ncols=hi - lo)
+        assert np.array_equal(s, solid[:, lo:hi]) and np.array_equal(r, refl[:, lo:hi])
+        cover += x1 - x0
+    assert cover == W
+    c = syn.fp_constants(H)
+    st = syn.fp_initial_state(solid, c)
+    P = orc.make_params(H, W, tau=c["tau"], gamma=c["gamma"], a=c["a"], kappa=c["kappa"], Eta_n=c["Eta_n"], M=c["M"],
+                        psi_wall=c["psi_wall"])
+    ref = orc.fp_initial_state(P, solid == 0)
+    for k in ("f", "g", "psi", "rho", "ux", "uy", "p", "mu", "mix_tau"):
+        assert np.array_equal(st[k], ref[k]), k
+    # a slab's initial state is the same columns
+    x0, x1 = slab_bounds(W, 3, 1)
+    st1 = syn.fp_initial_state(np.ascontiguousarray(solid[:, x0:x1]), c, col0=x0)
+    assert np.array_equal(st1["f"], st["f"][:, :, x0:x1]) and np.array_equal(st1["psi"], st["psi"][:, x0:x1])
+
+
+def test_fp_constants_match_reference_fixture(golden):
+    """the restated constant block of fingering_periodic.py:15-40 gives the reference's floats exactly"""
+    from fingering_dynamics_b200 import synthetic as syn
+    d = golden("fp_full_scalars")
+    c = syn.fp_constants(400)
+    for k in ("tau", "gamma", "a", "kappa", "Eta_n", "M", "u0", "psi_wall"):
+        assert c[k] == float(d["c_" + k]), k
+    assert np.array_equal(c["inlet_ux"], d["inlet_ux"])
