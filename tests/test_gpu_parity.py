@@ -43,6 +43,10 @@ def test_trajectory_matches_reference_fixtures(golden, name, kernel):
         e.step(step - done)
         done = step
         names = [k for k in hp.ALL_FIELDS if "s%d_%s" % (step, k) in d and (pops or k not in ("f", "g"))]
+        if name.startswith("va_"):
+            # validation.py:396 refreshes mix_tau at the START of an iteration, so the value it holds after
+            # n iterations belongs to state n-1; the engine reports tau_mix of state n.  Not a state variable.
+            names.remove("mix_tau")
         got = e.get_state(names)
         _compare(got, d, "s%d" % step, names, TOL64, mask)
     assert e.iterations == 40
