@@ -102,7 +102,8 @@ def lib():
     """The loaded CUDA library.  Raises if it is missing and cannot be built: there is no fallback."""
     global _lib
     if _lib is None:
-        path = build()
+        # FDLBM_LIB: load a specific build of the same sources (kernel tuning experiments)
+        path = os.environ.get("FDLBM_LIB") or build()
         L = ctypes.CDLL(path)
         for name, (res, args) in _SIGS.items():
             fn = getattr(L, name)

@@ -76,20 +76,31 @@ __device__ __forceinline__ void pull(const LbmParams<T> &P, int xl, int y, int b
     const T *c0 = P.src + lat_idx(Hp, xl, base, 0);
     const T *cm = c0 - (size_t)NPOP * Hp;  // column x-1: source of e_x = +1
     const T *cp = c0 + (size_t)NPOP * Hp;  // column x+1: source of e_x = -1
-    v[0] = c0[y];
-    v[1] = cm[1 * Hp + y];
-    v[2] = c0[2 * Hp + ym];
-    v[3] = cp[3 * Hp + y];
-    v[4] = c0[4 * Hp + yp];
-    v[5] = cm[5 * Hp + ym];
-    v[6] = cp[6 * Hp + ym];
-    v[7] = cp[7 * Hp + yp];
-    v[8] = cm[8 * Hp + yp];
+    // streamed source of each direction
+    const T *s1 = cm + 1 * Hp + y, *s2 = c0 + 2 * Hp + ym, *s3 = cp + 3 * Hp + y, *s4 = c0 + 4 * Hp + yp;
+    const T *s5 = cm + 5 * Hp + ym, *s6 = cp + 6 * Hp + ym, *s7 = cp + 7 * Hp + yp, *s8 = cm + 8 * Hp + yp;
     if (bits) {
-#pragma unroll
-        for (int i = 1; i < 9; ++i)
-            if ((bits >> (i - 1)) & 1u) v[i] = c0[opp(i) * Hp + y];
+        // bounced-back directions read the opposite population of the cell itself: select the ADDRESS, so
+        // that every register is the target of exactly one load (no write-after-write wait on a load in flight)
+        const T *o = c0 + y;
+        if (bits & 0x01u) s1 = o + 3 * Hp;
+        if (bits & 0x02u) s2 = o + 4 * Hp;
+        if (bits & 0x04u) s3 = o + 1 * Hp;
+        if (bits & 0x08u) s4 = o + 2 * Hp;
+        if (bits & 0x10u) s5 = o + 7 * Hp;
+        if (bits & 0x20u) s6 = o + 8 * Hp;
+        if (bits & 0x40u) s7 = o + 5 * Hp;
+        if (bits & 0x80u) s8 = o + 6 * Hp;
     }
+    v[0] = c0[y];
+    v[1] = *s1;
+    v[2] = *s2;
+    v[3] = *s3;
+    v[4] = *s4;
+    v[5] = *s5;
+    v[6] = *s6;
+    v[7] = *s7;
+    v[8] = *s8;
 }
 
 // Zou-He rules for g on the faces (fingering_periodic.py:278-324, fingering.py:305-390).

@@ -5,25 +5,46 @@
 // sum of g pulled from ITS neighbours (two-ring dependency, SURVEY.md finding 5).  Instead of staging
 // psi_new through HBM (+30% traffic), a CTA owns a strip of TY consecutive y and MARCHES along x:
 //
-//   * column records are streamed from HBM into shared-memory stage rings with cp.async (16-byte
-//     chunks, D columns ahead of the compute front), so the loads of the next columns are in flight
-//     while the current column is being collided and no registers are tied up by them;
-//   * iteration x:  wait for column x+2 -> pull g of column x+1 from the stages (+ bounce-back, Zou-He)
-//     -> psi_new(x+1, .) into a 4-slot psi ring (plus the strip's two halo cells), barrier,
-//     pull f of column x, moments, stencils from psi ring rows x-1, x, x+1, collide with the g pulled
-//     one iteration earlier (kept in registers), store the 18 populations of column x (coalesced).
+//   * the g columns are streamed from HBM into a shared-memory stage ring with cp.async (16-byte
+//     chunks, D columns ahead of the compute front): the loads of the next columns are in flight while
+//     the current column is collided, and the strip's neighbours in y are reachable for the psi halo;
+//   * the f columns are either staged the same way (STAGE_F) or pulled straight into registers at the
+//     top of the iteration from lines that were prefetched into L2 a few columns ahead;
+//   * iteration x:  wait for g column x+2 (the only barrier) -> pull g of column x+1 from the stages
+//     (+ bounce-back, Zou-He) -> psi_new(x+1, y); rows y-1 / y+1 arrive by WARP SHUFFLE from the
+//     neighbouring lanes (the two end lanes of a warp evaluate their outer neighbour themselves), the
+//     3x3 psi neighbourhood lives in registers and rotates with x -> moments of column x, stencils,
+//     collide with the g pulled one iteration earlier, store the 18 populations of column x (coalesced).
 //
-// Work is the linearised list of (y strip, column) pairs cut into equal contiguous chunks, one per CTA,
-// with exactly one resident wave (grid = SMs x CTAs/SM), so there is no tail and the pipeline warm-up
-// (a few extra column loads, L2 hits) is paid once per chunk.  The y wrap is resolved when a stage is
-// filled; the x wrap / slab halo comes from the two ghost columns.
+// Scheduling: one resident wave.  Strips are the fast CTA index, so the CTAs working on the same column
+// range advance in step and the apron rows a strip reads are L2 hits on lines its neighbour streams.
+// The y wrap is resolved when a stage is filled; the x wrap / slab halo comes from the ghost columns.
 #pragma once
 #include "lbm_device.cuh"
 
 namespace fdlbm {
 
-constexpr int FUSED_TY = 128;  // rows per strip = threads per CTA
-constexpr int FUSED_D = 2;     // prefetch distance in columns
+#ifndef FDLBM_FUSED_TY
+#define FDLBM_FUSED_TY 128
+#endif
+#ifndef FDLBM_FUSED_D
+#define FDLBM_FUSED_D 2
+#endif
+// resident CTAs per SM the register allocation is bounded for: fp64 needs ~166 registers to stay free of
+// spills (3 CTAs = 12 warps, 48 KB of stages each); fp32 fits 128 registers (4 CTAs)
+#ifndef FDLBM_FUSED_MINB64
+#define FDLBM_FUSED_MINB64 3
+#endif
+#ifndef FDLBM_FUSED_MINB32
+#define FDLBM_FUSED_MINB32 4
+#endif
+#ifndef FDLBM_STAGE_F
+#define FDLBM_STAGE_F 0
+#endif
+constexpr int FUSED_TY = FDLBM_FUSED_TY;  // rows per strip = threads per CTA
+constexpr int FUSED_D = FDLBM_FUSED_D;    // cp.async prefetch distance in columns
+constexpr bool FUSED_STAGE_F = FDLBM_STAGE_F != 0;
+constexpr int FUSED_L2_AHEAD = 3;         // L2 prefetch distance of the f columns (registers path)
 
 __device__ __forceinline__ void cp_async16(void *smem, const void *gmem)
 {
@@ -41,238 +62,252 @@ __device__ __forceinline__ void cp_async_wait()
 {
     asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory");
 }
+__device__ __forceinline__ void prefetch_l2(const void *p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
 
-template <typename T, int TY>
+template <typename T, int TY, bool STAGE_F>
 struct FusedCfg {
     static constexpr int HALO = 16 / (int)sizeof(T);      // rows of apron per side: keeps 16-byte chunks aligned
     static constexpr int PT = TY + 2 * HALO;              // stage row pitch (elements)
-    static constexpr int NS = 3 + FUSED_D;                // stages per ring (f: x-1..x+1+D, g: x..x+2+D)
+    static constexpr int NS = 3 + FUSED_D;                // stages per ring (g: x..x+2+D, f: x-1..x+1+D)
     static constexpr int FAM = 9 * PT;                    // elements of one stage (one family of one column)
-    static constexpr int RING = TY + 2;                   // psi ring row: y0-1 .. y0+TY
-    static constexpr size_t SMEM = (size_t)(2 * NS * FAM + 4 * RING) * sizeof(T);
+    static constexpr size_t SMEM = (size_t)((STAGE_F ? 2 : 1) * NS * FAM) * sizeof(T);
 };
 
-// Fill one stage: family `base` (0: f, 9: g) of local column c, rows [y0-HALO, y0+rows+HALO) with the y wrap
-// applied.  16-byte cp.async for chunks that are contiguous in memory, element-wise otherwise.
-template <typename T, int TY>
-__device__ __forceinline__ void stage_fill(const LbmParams<T> &P, T *stage, int c, int base, int y0, int rows)
+// Fill one stage: 9 populations of one family of the column whose record starts at `col` (pop 0 of the
+// family), rows [y0-HALO, y0+rows+HALO) with the y wrap applied.  16-byte cp.async where the chunk is
+// contiguous in memory, element-wise at the wrap.
+template <typename T, int TY, int PT, int HALO>
+__device__ __forceinline__ void stage_fill(T *stage, const T *col, int Hp, int H, int y0, int rows)
 {
-    using C = FusedCfg<T, TY>;
     constexpr int EPC = 16 / (int)sizeof(T);  // elements per chunk
-    const int nch = (rows + 2 * C::HALO + EPC - 1) / EPC;
-    const T *col = P.src + lat_idx(P.Hp, c, base, 0);
+    const int nch = (rows + 2 * HALO + EPC - 1) / EPC;
     for (int ch = threadIdx.x; ch < nch; ch += TY) {
         const int r0 = ch * EPC;
-        const int y = y0 - C::HALO + r0;
-        if (y >= 0 && y + EPC <= P.H) {
+        const int y = y0 - HALO + r0;
+        if (y >= 0 && y + EPC <= H) {
 #pragma unroll
-            for (int pop = 0; pop < 9; ++pop) cp_async16(stage + pop * C::PT + r0, col + (size_t)pop * P.Hp + y);
+            for (int pop = 0; pop < 9; ++pop) cp_async16(stage + pop * PT + r0, col + (size_t)pop * Hp + y);
         } else {
 #pragma unroll
             for (int e = 0; e < EPC; ++e) {
-                int yy = (y + e) % P.H;
-                if (yy < 0) yy += P.H;
+                int yy = (y + e) % H;
+                if (yy < 0) yy += H;
 #pragma unroll
                 for (int pop = 0; pop < 9; ++pop)
-                    cp_async_small<(int)sizeof(T)>(stage + pop * C::PT + r0 + e, col + (size_t)pop * P.Hp + yy);
+                    cp_async_small<(int)sizeof(T)>(stage + pop * PT + r0 + e, col + (size_t)pop * Hp + yy);
             }
         }
     }
 }
 
-// pull-stream + bounce-back from the stage rings: v_i <- stage_i(column c - e_x)[row j - e_y]
+// pull-stream + bounce-back from three stages: v_i <- stage_i(column c - e_x)[row j - e_y]
 template <typename T, int PT>
 __device__ __forceinline__ void pull_staged(const T *sm, const T *s0, const T *sp, int j, unsigned bits, T v[9])
 {
-    v[0] = s0[j];
-    v[1] = sm[1 * PT + j];
-    v[2] = s0[2 * PT + j - 1];
-    v[3] = sp[3 * PT + j];
-    v[4] = s0[4 * PT + j + 1];
-    v[5] = sm[5 * PT + j - 1];
-    v[6] = sp[6 * PT + j - 1];
-    v[7] = sp[7 * PT + j + 1];
-    v[8] = sm[8 * PT + j + 1];
-    if (bits) {
-#pragma unroll
-        for (int i = 1; i < 9; ++i)
-            if ((bits >> (i - 1)) & 1u) v[i] = s0[opp(i) * PT + j];
+    const T *s1 = sm + 1 * PT + j, *s2 = s0 + 2 * PT + j - 1, *s3 = sp + 3 * PT + j, *s4 = s0 + 4 * PT + j + 1;
+    const T *s5 = sm + 5 * PT + j - 1, *s6 = sp + 6 * PT + j - 1, *s7 = sp + 7 * PT + j + 1, *s8 = sm + 8 * PT + j + 1;
+    if (bits) {  // bounced-back directions: select the address (one load per register)
+        const T *o = s0 + j;
+        if (bits & 0x01u) s1 = o + 3 * PT;
+        if (bits & 0x02u) s2 = o + 4 * PT;
+        if (bits & 0x04u) s3 = o + 1 * PT;
+        if (bits & 0x08u) s4 = o + 2 * PT;
+        if (bits & 0x10u) s5 = o + 7 * PT;
+        if (bits & 0x20u) s6 = o + 8 * PT;
+        if (bits & 0x40u) s7 = o + 5 * PT;
+        if (bits & 0x80u) s8 = o + 6 * PT;
     }
+    v[0] = s0[j];
+    v[1] = *s1;
+    v[2] = *s2;
+    v[3] = *s3;
+    v[4] = *s4;
+    v[5] = *s5;
+    v[6] = *s6;
+    v[7] = *s7;
+    v[8] = *s8;
 }
 
-template <typename T, int TY>
-__global__ void __launch_bounds__(TY) k_fused(const __grid_constant__ LbmParams<T> P, int nyt, int chunk)
+struct RawFlags {
+    unsigned refl, word;  // reflect byte and solid-mask word exactly as loaded
+};
+
+template <typename T, int TY, bool STAGE_F>
+__global__ void __launch_bounds__(TY, sizeof(T) == 8 ? FDLBM_FUSED_MINB64 : FDLBM_FUSED_MINB32) k_fused(const __grid_constant__ LbmParams<T> P, int nyt, int chunk)
 {
-    using C = FusedCfg<T, TY>;
-    constexpr int D = FUSED_D, NS = C::NS, PT = C::PT, HALO = C::HALO;
+    using C = FusedCfg<T, TY, STAGE_F>;
+    constexpr int D = FUSED_D, NS = C::NS, PT = C::PT, HALO = C::HALO, FAM = C::FAM;
+    constexpr unsigned FULL = 0xffffffffu;
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    T *fst = reinterpret_cast<T *>(smem_raw);   // [NS][9][PT]
-    T *gst = fst + NS * C::FAM;                 // [NS][9][PT]
-    T *ring = gst + NS * C::FAM;                // [4][RING]
-    const int t = threadIdx.x;
+    T *gst = reinterpret_cast<T *>(smem_raw);        // [NS][9][PT]
+    T *fst = gst + NS * FAM;                         // [NS][9][PT] when STAGE_F
+    const int t = threadIdx.x, lane = t & 31;
+    const int H = P.H, Hp = P.Hp;
+
+    const int yt = blockIdx.x % nyt;
+    const int xs = (blockIdx.x / nyt) * chunk;
+    const int xe = min(P.Wl, xs + chunk);
+    const int y0 = yt * TY;
+    const int y = y0 + t;
+    const int ny = min(TY, H - y0);
+    const bool active = t < ny;
+    const int j = t + HALO;  // stage row of this thread's cell
+
+    // psi of the rows y-1 / y+1 comes from the neighbouring lanes by warp shuffle.  The first and last
+    // active lane of a warp have no such neighbour: they evaluate psi of that row themselves (same
+    // staged data, one extra pull for two lanes per warp), so warps never wait for each other.
+    const bool edge_lo = active && lane == 0;
+    const bool edge_hi = active && (lane == 31 || t == ny - 1);
+    const bool edge = edge_lo || edge_hi, edge2 = edge_lo && edge_hi;
+    auto wrap_row = [&](int yy) {  // wrapped global row, or -1 for a ghost row of a y-wall variant
+        if (yy < 0 || yy >= H) return P.y_wall ? -1 : (yy < 0 ? yy + H : yy - H);
+        return yy;
+    };
+    const int ye1 = wrap_row(edge_lo ? y - 1 : y + 1), je1 = edge_lo ? j - 1 : j + 1;
+    const int ye2 = wrap_row(y + 1), je2 = j + 1;  // second neighbour of a one-row warp (edge2)
+
     auto slot = [](int c) { return ((c % NS) + NS) % NS; };
+    auto in_domain = [&](int c) { return P.x_periodic || (P.gx0 + c >= 0 && P.gx0 + c < P.W); };
 
-    // CTA b marches over columns [xs, xe) of strip yt.  Strips are the FAST index: the nyt CTAs that work
-    // on the same column range start together and advance in step, so the apron rows a strip reads
-    // (HALO rows of its neighbours) are L2 hits on lines the neighbour strip is streaming anyway.
-    {
-        const int yt = blockIdx.x % nyt;
-        const int xs = (blockIdx.x / nyt) * chunk;
-        const int xe = min(P.Wl, xs + chunk);
-
-        const int y0 = yt * TY;
-        const int y = y0 + t;
-        const int ny = min(TY, P.H - y0);
-        const bool active = t < ny;
-        const int j = t + HALO;                          // stage row of this thread's cell
-        const int y_halo = t == 0 ? y0 - 1 : y0 + ny;    // lanes 0 and 1 also serve the strip's halo cells
-        const int j_halo = t == 0 ? HALO - 1 : HALO + ny;
-        const int s_halo = t == 0 ? 0 : ny + 1;
-
-        // one pipeline step: g column v+2+D and f column v+1+D (only the columns this run will read)
-        auto prefetch = [&](int v) {
-            const int cg = v + 2 + D, cf = v + 1 + D;
-            if (cg >= xs - 2 && cg <= xe + 1) stage_fill<T, TY>(P, gst + slot(cg) * C::FAM, cg, 9, y0, ny);
-            if (cf >= xs - 1 && cf <= xe) stage_fill<T, TY>(P, fst + slot(cf) * C::FAM, cf, 0, y0, ny);
-            cp_async_commit();
-        };
-        // Per-cell flags are plain global loads issued two columns ahead of their use and carried RAW in
-        // registers (reflect byte, solid-mask word): nothing depends on them until they are decoded two
-        // iterations later, so their latency never sits on the critical path.
-        struct RawFlags {
-            unsigned refl, word;
-        };
-        auto load_flags = [&](int c, int yy) -> RawFlags {
-            RawFlags r{0u, 0u};
-            if (c > xe + 1) return r;
-            if (yy < 0 || yy >= P.H) {
-                if (P.y_wall) return r;
-                yy = yy < 0 ? yy + P.H : yy - P.H;
-            }
-            const int gx = P.gx0 + c;
-            if (!P.x_periodic && (gx < 0 || gx >= P.W)) return r;
-            r.refl = P.reflect[cell_idx(P.Hp, c, yy)];
-            r.word = P.solid[(size_t)(c + G) * (P.Hp >> 5) + (yy >> 5)];
-            return r;
-        };
-        // decode for the cell in global row yy: reflect bits | solid << 8
-        auto decode = [&](RawFlags r, int yy) -> unsigned {
-            if (yy < 0) yy += P.H;
-            if (yy >= P.H) yy -= P.H;
-            return r.refl | (((r.word >> (yy & 31)) & 1u) << 8);
-        };
-        // psi_new of (column c, stage row jj / global row yy) from the g stages
-        auto psi_staged = [&](int c, int yy, int jj, unsigned flags, T g[9]) -> T {
-            if (yy < 0 || yy >= P.H) {
-                if (P.y_wall) return P.psi_wall;
-                yy = yy < 0 ? yy + P.H : yy - P.H;
-            }
-            const int gx = P.gx0 + c;
-            if (!P.x_periodic) {
-                if (gx < 0) return P.psi_left;
-                if (gx >= P.W) return P.psi_right;
-            }
-            pull_staged<T, PT>(gst + slot(c - 1) * C::FAM, gst + slot(c) * C::FAM, gst + slot(c + 1) * C::FAM, jj,
-                               flags & 0xffu, g);
-            if (P.zou_he && (gx == 0 || gx == P.W - 1)) zou_he_g(P, gx, yy, g);
-            if (flags & 0x100u) return P.psi_wall;
-            return (((g[0] + g[1]) + (g[2] + g[3])) + ((g[4] + g[5]) + (g[6] + g[7]))) + g[8];
-        };
-
-        T g_cur[9], g_nxt[9], psi_cur = T(0), psi_nxt = T(0);
-        unsigned fl_cur = 0, fl_nxt = 0;             // flags of this thread's cell in columns x, x+1
-        RawFlags fq0{0, 0}, fq1{0, 0}, hq0{0, 0}, hq1{0, 0};  // look-ahead queues: own / halo cell, columns x+1, x+2
-
-        // pipeline warm-up.  Steps v = xs-4-D .. xs-2 bring in g columns xs-2 .. xs+D (all NS slots) and
-        // f columns xs-1 .. xs-1+D; psi(xs-1) needs g columns xs-2..xs, then g column xs-2 makes room.
-        for (int v = xs - 4 - D; v < xs - 1; ++v) prefetch(v);
-        const RawFlags z{0, 0};
-        const RawFlags rf_m1 = active ? load_flags(xs - 1, y) : z, rh_m1 = t < 2 ? load_flags(xs - 1, y_halo) : z;
-        const RawFlags rf_0 = active ? load_flags(xs, y) : z, rh_0 = t < 2 ? load_flags(xs, y_halo) : z;
-        if (active) {
-            fq0 = load_flags(xs + 1, y);
-            fq1 = load_flags(xs + 2, y);
+    // one pipeline step: g column v+2+D (and f column v+1+D when staged); only columns this run reads
+    auto prefetch = [&](int v) {
+        const int cg = v + 2 + D, cf = v + 1 + D;
+        if (cg >= xs - 2 && cg <= xe + 1)
+            stage_fill<T, TY, PT, HALO>(gst + slot(cg) * FAM, P.src + lat_idx(Hp, cg, 9, 0), Hp, H, y0, ny);
+        if (STAGE_F && cf >= xs - 1 && cf <= xe)
+            stage_fill<T, TY, PT, HALO>(fst + slot(cf) * FAM, P.src + lat_idx(Hp, cf, 0, 0), Hp, H, y0, ny);
+        cp_async_commit();
+    };
+    // Per-cell flags are plain global loads issued two columns ahead of their use and carried RAW in
+    // registers: nothing depends on them until they are decoded two iterations later, so their latency
+    // never sits on the critical path.
+    auto load_flags = [&](int c, int yy) -> RawFlags {
+        RawFlags r{0u, 0u};
+        if (c > xe + 1 || yy < 0 || !in_domain(c)) return r;
+        r.refl = P.reflect[cell_idx(Hp, c, yy)];
+        r.word = P.solid[(size_t)(c + G) * (Hp >> 5) + (yy >> 5)];
+        return r;
+    };
+    auto decode = [](RawFlags r, int yy) -> unsigned {  // reflect bits | solid << 8
+        return r.refl | (((r.word >> (yy & 31)) & 1u) << 8);
+    };
+    // psi_new of the cell (column c, global row yy >= 0 already wrapped, stage row jj) from the g stages
+    auto psi_staged = [&](int c, int yy, int jj, unsigned flags, T g[9]) -> T {
+        if (yy < 0) return P.psi_wall;
+        const int gx = P.gx0 + c;
+        if (!P.x_periodic) {
+            if (gx < 0) return P.psi_left;
+            if (gx >= P.W) return P.psi_right;
         }
-        if (t < 2) {
-            hq0 = load_flags(xs + 1, y_halo);
-            hq1 = load_flags(xs + 2, y_halo);
-        }
-        cp_async_wait<D>();  // g columns <= xs have landed (this thread's share)
-        __syncthreads();
-        {
+        pull_staged<T, PT>(gst + slot(c - 1) * FAM, gst + slot(c) * FAM, gst + slot(c + 1) * FAM, jj, flags & 0xffu, g);
+        if (P.zou_he && (gx == 0 || gx == P.W - 1)) zou_he_g(P, gx, yy, g);
+        if (flags & 0x100u) return P.psi_wall;
+        return (((g[0] + g[1]) + (g[2] + g[3])) + ((g[4] + g[5]) + (g[6] + g[7]))) + g[8];
+    };
+    // psi_new of column c on rows y-1, y, y+1 (q_m, q_0, q_p); the pulled g of the own cell is returned
+    auto psi_column = [&](int c, unsigned fl_own, RawFlags fl_edge, T g[9], T &q_m, T &q_0, T &q_p) {
+        q_0 = T(0);
+        if (active) q_0 = psi_staged(c, y, j, fl_own, g);
+        T e1 = T(0), e2 = T(0);
+        if (edge) {
             T gh[9];
-            T *row = ring + ((xs - 1 + 4) & 3) * C::RING;
-            if (active) row[t + 1] = psi_staged(xs - 1, y, j, decode(rf_m1, y), gh);
-            if (t < 2) row[s_halo] = psi_staged(xs - 1, y_halo, j_halo, decode(rh_m1, y_halo), gh);
+            e1 = psi_staged(c, ye1, je1, decode(fl_edge, ye1), gh);
+            if (edge2) e2 = psi_staged(c, ye2, je2, decode(load_flags(c, ye2), ye2), gh);
         }
-        __syncthreads();
-        prefetch(xs - 1);
-        cp_async_wait<D>();  // g column xs+1 has landed
-        __syncthreads();
-        {
-            T gh[9];
-            T *row = ring + (xs & 3) * C::RING;
-            fl_cur = decode(rf_0, y);
-            if (active) row[t + 1] = psi_cur = psi_staged(xs, y, j, fl_cur, g_cur);
-            if (t < 2) row[s_halo] = psi_staged(xs, y_halo, j_halo, decode(rh_0, y_halo), gh);
-        }
+        const T dn = __shfl_up_sync(FULL, q_0, 1), up = __shfl_down_sync(FULL, q_0, 1);
+        q_m = edge_lo ? e1 : dn;
+        q_p = edge_hi ? (edge_lo ? e2 : e1) : up;
+    };
 
-        for (int x = xs; x < xe; ++x) {
-            cp_async_wait<D - 1>();  // g column x+2 and f column x+1 have landed
-            __syncthreads();         // ... for every thread; and everybody is done with iteration x-1
-            prefetch(x);             // overwrites the stages of g column x-1 and f column x-2: no longer read
-            const RawFlags fq2 = active ? load_flags(x + 3, y) : z;       // decoded two iterations from now
-            const RawFlags hq2 = t < 2 ? load_flags(x + 3, y_halo) : z;
-            {
-                T gh[9];
-                T *row = ring + ((x + 1) & 3) * C::RING;
-                fl_nxt = decode(fq0, y);
-                if (active) row[t + 1] = psi_nxt = psi_staged(x + 1, y, j, fl_nxt, g_nxt);
-                if (t < 2) row[s_halo] = psi_staged(x + 1, y_halo, j_halo, decode(hq0, y_halo), gh);
-            }
-            __syncthreads();
-            if (active) {
-                T f[9];
-                pull_staged<T, PT>(fst + slot(x - 1) * C::FAM, fst + slot(x) * C::FAM, fst + slot(x + 1) * C::FAM, j,
-                                   fl_cur & 0xffu, f);
-                if (P.zou_he) {
-                    const int gx_ = P.gx0 + x;
-                    if (gx_ == 0 || gx_ == P.W - 1) zou_he_f(P, x, gx_, y, f, PullRow<T>());
-                }
-                if (!(fl_cur & 0x100u)) {
-                    const T *rm = ring + ((x - 1 + 4) & 3) * C::RING + t + 1, *r0 = ring + (x & 3) * C::RING + t + 1,
-                            *rp = ring + ((x + 1) & 3) * C::RING + t + 1;
-                    T gx, gy, lap;
-                    //        C      E      W      N      S      NE     NW     SW      SE
-                    stencil9(psi_cur, rp[0], rm[0], r0[1], r0[-1], rp[1], rm[1], rm[-1], rp[-1], gx, gy, lap);
-                    Macro<T> m;
-                    moments(P, f, psi_cur, gx, gy, lap, m);
-                    collide(P, m, f, g_cur);
-                }
-                store_cell(P, x, y, f, g_cur);
-                if (P.zou_he) {  // the next step's Zou-He needs grad psi and mu at the face columns
-                    const int gx_ = P.gx0 + x;
-                    if (gx_ < 2 || gx_ >= P.W - 2) P.psi_new[cell_idx(P.Hp, x, y)] = psi_cur;
-                }
-            }
-#pragma unroll
-            for (int i = 0; i < 9; ++i) g_cur[i] = g_nxt[i];
-            psi_cur = psi_nxt;
-            fl_cur = fl_nxt;
-            fq0 = fq1;
-            fq1 = fq2;
-            hq0 = hq1;
-            hq1 = hq2;
-        }
-        cp_async_wait<0>();
+    T g_cur[9], g_nxt[9];
+    T pm_m, pm_0, pm_p, p0_m, p0_0, p0_p, pp_m, pp_0, pp_p;  // psi_new on columns x-1, x, x+1 x rows y-1, y, y+1
+    unsigned fl_cur = 0, fl_nxt = 0;                          // flags of this thread's cell in columns x, x+1
+    const RawFlags z{0u, 0u};
+    RawFlags fq0 = z, fq1 = z, eq0 = z, eq1 = z;               // look-ahead queues: own / edge-neighbour cell, columns x+1, x+2
+
+    // pipeline warm-up.  Steps v = xs-4-D .. xs-2 bring in g columns xs-2 .. xs+D (all NS slots);
+    // psi(xs-1) needs g columns xs-2..xs, then g column xs-2 makes room for column xs+1+D.
+    for (int v = xs - 4 - D; v < xs - 1; ++v) prefetch(v);
+    const RawFlags rf_m1 = active ? load_flags(xs - 1, y) : z, re_m1 = edge ? load_flags(xs - 1, ye1) : z;
+    const RawFlags rf_0 = active ? load_flags(xs, y) : z, re_0 = edge ? load_flags(xs, ye1) : z;
+    if (active) {
+        fq0 = load_flags(xs + 1, y);
+        fq1 = load_flags(xs + 2, y);
     }
+    if (edge) {
+        eq0 = load_flags(xs + 1, ye1);
+        eq1 = load_flags(xs + 2, ye1);
+    }
+    cp_async_wait<D>();  // g columns <= xs have landed (this thread's share)
+    __syncthreads();
+    psi_column(xs - 1, decode(rf_m1, y), re_m1, g_nxt, pm_m, pm_0, pm_p);
+    __syncthreads();
+    prefetch(xs - 1);
+    cp_async_wait<D>();  // g column xs+1 has landed
+    __syncthreads();
+    fl_cur = decode(rf_0, y);
+    psi_column(xs, fl_cur, re_0, g_cur, p0_m, p0_0, p0_p);
+
+    for (int x = xs; x < xe; ++x) {
+        cp_async_wait<D - 1>();  // g column x+2 (and staged f column x+1) have landed
+        __syncthreads();         // ... for every thread; and everybody is done with iteration x-1
+        prefetch(x);             // overwrites the stage of g column x-1 (f column x-2): no longer read
+        T f[9];
+        if (!STAGE_F) {
+            // f of column x straight into registers; consumed after the psi phase below
+            if (active) pull(P, x, y, 0, fl_cur & 0xffu, f);
+            // and the lines of f column x+L2_AHEAD into L2: one prefetch per 128-byte line of the strip
+            constexpr int LPP = (TY * (int)sizeof(T) + 127) / 128;  // lines per population row
+            const int cf = x + FUSED_L2_AHEAD;
+            const int tt = TY - 1 - t;  // the cp.async issue above kept the low warps busy: use the high ones
+            if (tt < 9 * LPP && cf <= xe + 1) {
+                const int pop = tt / LPP, ln = tt - pop * LPP;
+                const int yy = y0 + ln * (128 / (int)sizeof(T));
+                if (yy < H) prefetch_l2(P.src + lat_idx(Hp, cf, pop, yy));
+            }
+        }
+        const RawFlags fq2 = active ? load_flags(x + 3, y) : z;  // decoded two iterations from now
+        const RawFlags eq2 = edge ? load_flags(x + 3, ye1) : z;
+        fl_nxt = decode(fq0, y);
+        psi_column(x + 1, fl_nxt, eq0, g_nxt, pp_m, pp_0, pp_p);
+        if (active) {
+            if (STAGE_F)
+                pull_staged<T, PT>(fst + slot(x - 1) * FAM, fst + slot(x) * FAM, fst + slot(x + 1) * FAM, j, fl_cur & 0xffu, f);
+            if (P.zou_he) {
+                const int gx_ = P.gx0 + x;
+                if (gx_ == 0 || gx_ == P.W - 1) zou_he_f(P, x, gx_, y, f, PullRow<T>());
+            }
+            if (!(fl_cur & 0x100u)) {
+                T gx, gy, lap;
+                //        C     E     W     N     S     NE    NW    SW    SE
+                stencil9(p0_0, pp_0, pm_0, p0_p, p0_m, pp_p, pm_p, pm_m, pp_m, gx, gy, lap);
+                Macro<T> m;
+                moments(P, f, p0_0, gx, gy, lap, m);
+                collide(P, m, f, g_cur);
+            }
+            store_cell(P, x, y, f, g_cur);
+            if (P.zou_he) {  // the next step's Zou-He needs grad psi and mu at the face columns
+                const int gx_ = P.gx0 + x;
+                if (gx_ < 2 || gx_ >= P.W - 2) P.psi_new[cell_idx(Hp, x, y)] = p0_0;
+            }
+        }
+#pragma unroll
+        for (int i = 0; i < 9; ++i) g_cur[i] = g_nxt[i];
+        pm_m = p0_m, pm_0 = p0_0, pm_p = p0_p;
+        p0_m = pp_m, p0_0 = pp_0, p0_p = pp_p;
+        fl_cur = fl_nxt;
+        fq0 = fq1, fq1 = fq2;
+        eq0 = eq1, eq1 = eq2;
+    }
+    cp_async_wait<0>();
 }
 
 // returns 0 or a cudaError_t
 template <typename T>
 int launch_fused(const LbmParams<T> &P, cudaStream_t stream)
 {
-    using C = FusedCfg<T, FUSED_TY>;
+    using C = FusedCfg<T, FUSED_TY, FUSED_STAGE_F>;
+    auto kern = k_fused<T, FUSED_TY, FUSED_STAGE_F>;
     static int n_cta = 0;  // per instantiation; device properties do not change within a process
     if (n_cta == 0) {
         int dev = 0, sms = 0, occ = 0;
@@ -280,9 +315,9 @@ int launch_fused(const LbmParams<T> &P, cudaStream_t stream)
         if (e != cudaSuccess) return (int)e;
         e = cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
         if (e != cudaSuccess) return (int)e;
-        e = cudaFuncSetAttribute(k_fused<T, FUSED_TY>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::SMEM);
+        e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::SMEM);
         if (e != cudaSuccess) return (int)e;
-        e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_fused<T, FUSED_TY>, FUSED_TY, C::SMEM);
+        e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, FUSED_TY, C::SMEM);
         if (e != cudaSuccess) return (int)e;
         if (occ < 1) occ = 1;
         n_cta = sms * occ;
@@ -294,7 +329,7 @@ int launch_fused(const LbmParams<T> &P, cudaStream_t stream)
     int chunk = (P.Wl + nchunks - 1) / nchunks;
     if (chunk < 8) chunk = 8;
     nchunks = (P.Wl + chunk - 1) / chunk;
-    k_fused<T, FUSED_TY><<<nyt * nchunks, FUSED_TY, C::SMEM, stream>>>(P, nyt, chunk);
+    kern<<<nyt * nchunks, FUSED_TY, C::SMEM, stream>>>(P, nyt, chunk);
     return 0;
 }
 
