@@ -45,11 +45,16 @@ class ClockSampler:
 
     def __init__(self, index=0):
         self.rows, self.proc, self.index = [], None, index
+        self.t_mark = None
+
+    def mark(self):
+        """start of the timed region: only samples taken after this call are summarised"""
+        self.t_mark = time.time()
 
     def __enter__(self):
         try:
             self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
-                                          "--format=csv,noheader,nounits", "-lms", "100"], stdout=subprocess.PIPE,
+                                          "--format=csv,noheader,nounits", "-lms", "50"], stdout=subprocess.PIPE,
                                          stderr=subprocess.DEVNULL, text=True)
             self.thr = threading.Thread(target=self._read, daemon=True)
             self.thr.start()
@@ -59,7 +64,7 @@ class ClockSampler:
 
     def _read(self):
         for line in self.proc.stdout:
-            self.rows.append([c.strip() for c in line.split(",")])
+            self.rows.append((time.time(), [c.strip() for c in line.split(",")]))
 
     def __exit__(self, *exc):
         if self.proc:
@@ -70,7 +75,10 @@ class ClockSampler:
     def summary(self):
         sm, mx, reasons = [], [], set()
         names = ("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap")
-        for r in self.rows:
+        rows = [r for (ts, r) in self.rows if self.t_mark is None or ts >= self.t_mark]
+        if len(rows) < 3:
+            rows = [r for (ts, r) in self.rows][-5:]
+        for r in rows:
             try:
                 sm.append(float(r[0]))
                 mx.append(float(r[1]))
@@ -129,7 +137,7 @@ def reference_arm(args):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=200)
+    ap.add_argument("--steps", type=int, default=400)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--dtype", default="f64", choices=["f64", "f32"])
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
@@ -180,12 +188,12 @@ def main():
 
     # ---- device-resident throughput ("value") -------------------------------------------------------
     eng.set_state(col0=x0, **st)
-    runner.step(Wm)
-    barrier()
-    l0 = eng.launch_count
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    with ClockSampler(local) as clocks:
+    with ClockSampler(local) as clocks:   # nvidia-smi needs a moment to start: launch it before the warm-up
+        runner.step(Wm)
         barrier()
+        l0 = eng.launch_count
+        clocks.mark()
         ev0.record(stream)
         runner.step(K)
         ev1.record(stream)

@@ -1,0 +1,147 @@
+"""Slab decomposition (fingering_dynamics_b200/slab.py).
+
+CPU (gloo, world_size 2): the halo-exchange protocol of SlabRunner -- neighbour selection, send/recv pairing,
+ring closing -- driven with a tiny NumPy stepper that, like the real step, needs two ghost columns per side.
+GPU: two engines on one device exchanging their halo blocks reproduce the single-slab run bit for bit.
+"""
+import os
+import sys
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_slab_bounds_cover_the_grid():
+    from fingering_dynamics_b200.slab import slab_bounds
+    for W, n in ((8192, 8), (400, 3), (17, 4), (65536, 8)):
+        edges = [slab_bounds(W, n, r) for r in range(n)]
+        assert edges[0][0] == 0 and edges[-1][1] == W
+        assert all(edges[r][1] == edges[r + 1][0] for r in range(n - 1))
+        sizes = [b - a for a, b in edges]
+        assert max(sizes) - min(sizes) <= 1
+
+
+class ToyEngine:
+    """columns [x0,x1) of a (H, W) field plus 2 ghost columns per side; one step = a 5-point-wide
+    stencil in x (needs BOTH ghost columns) followed by a roll in y."""
+
+    def __init__(self, full, x0, x1):
+        import torch
+        self.x0, self.x1 = x0, x1
+        H = full.shape[0]
+        self.a = torch.zeros((x1 - x0 + 4, H), dtype=torch.float64)   # [column][row]: halo blocks are contiguous
+        self.a[2:-2] = torch.from_numpy(full[:, x0:x1].T.copy())
+
+    def halo_tensors(self):
+        return self.a[2:4], self.a[0:2], self.a[-4:-2], self.a[-2:]
+
+    def step(self, n):
+        import torch
+        for _ in range(n):
+            a = self.a
+            new = a.clone()
+            new[2:-2] = 0.4 * a[2:-2] + 0.2 * (a[1:-3] + a[3:-1]) + 0.1 * (a[0:-4] + a[4:])
+            self.a = torch.roll(new, 1, dims=1)
+
+    def get_state(self, names=None, **kw):
+        return self.a[2:-2].numpy().T.copy()
+
+
+def _toy_reference(full, n, periodic):
+    a = full.copy()
+    for _ in range(n):
+        if periodic:
+            p = np.concatenate([a[:, -2:], a, a[:, :2]], axis=1)
+        else:
+            p = np.pad(a, ((0, 0), (2, 2)))
+        a = 0.4 * p[:, 2:-2] + 0.2 * (p[:, 1:-3] + p[:, 3:-1]) + 0.1 * (p[:, 0:-4] + p[:, 4:])
+        a = np.roll(a, 1, axis=0)
+    return a
+
+
+def _worker(rank, world, port, periodic, q):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    sys.path.insert(0, ROOT)
+    import torch.distributed as dist
+    from fingering_dynamics_b200.slab import SlabRunner, slab_bounds
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    rng = np.random.default_rng(5)
+    full = rng.random((6, 23))
+    x0, x1 = slab_bounds(23, world, rank)
+    eng = ToyEngine(full, x0, x1)
+    run = SlabRunner(eng, rank, world, periodic=periodic)
+    run.step(4)
+    out = run.get_state()
+    ref = _toy_reference(full, 4, periodic)[:, x0:x1]
+    q.put((rank, bool(np.array_equal(out, ref)), float(np.abs(out - ref).max())))
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("periodic", [False, True])
+def test_halo_exchange_protocol_gloo_world2(periodic):
+    import torch.multiprocessing as mp
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 29500 + (os.getpid() % 500) + (7 if periodic else 0)
+    procs = [ctx.Process(target=_worker, args=(r, 2, port, periodic, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = [q.get(timeout=120) for _ in procs]
+    for p in procs:
+        p.join(timeout=60)
+    for rank, ok, err in res:
+        assert ok, "rank %d differs from the single-domain run by %g" % (rank, err)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("name,nslab", [("fp_small", 2), ("fp_small", 3), ("fg_small", 2), ("va_small", 2)])
+def test_slabs_on_one_gpu_are_bit_identical_to_the_single_slab_run(golden, name, nslab):
+    """N engines (slabs) on one device, halos moved with device copies: same bits as one engine."""
+    import torch
+    from tests import helpers as hp
+    from fingering_dynamics_b200.slab import slab_bounds, _DevBuf
+    d = golden(name)
+    W = int(d["W"])
+    periodic = name.startswith("va")
+    s0 = hp.state_for_engine(d, "s0")
+    ref = hp.ENGINES[name](d)
+    ref.set_state(**s0)
+    ref.step(12)
+    want = ref.get_state(("f", "g", "psi", "rho", "ux", "uy"))
+    ref.close()
+
+    engs = []
+    for r in range(nslab):
+        e = hp.ENGINES[name](d, slab=slab_bounds(W, nslab, r), external_halo=True)
+        e.set_state(**s0)
+        engs.append(e)
+    dev = torch.device("cuda", 0)
+
+    def view(ptr, n):
+        return torch.as_tensor(_DevBuf(ptr, n), device=dev)
+
+    def exchange():
+        for e in engs:
+            e.sync()
+        hs = [e.halo_regions() for e in engs]
+        for r in range(nslab):
+            right = r + 1 if r + 1 < nslab else (0 if periodic else None)
+            if right is None:
+                continue
+            view(hs[right].recv_lo, hs[r].bytes).copy_(view(hs[r].send_hi, hs[r].bytes))
+            view(hs[r].recv_hi, hs[r].bytes).copy_(view(hs[right].send_lo, hs[r].bytes))
+        torch.cuda.synchronize()
+
+    for _ in range(12):
+        exchange()
+        for e in engs:
+            e.step(1)
+    exchange()
+    for r, e in enumerate(engs):
+        x0, x1 = slab_bounds(W, nslab, r)
+        got = e.get_state(("f", "g", "psi", "rho", "ux", "uy"))
+        for k in got:
+            assert np.array_equal(got[k], want[k][..., x0:x1]), (name, r, k)
+        e.close()
