@@ -91,6 +91,8 @@ _SIGS = {
     "fdlbm_op_stencils": (ctypes.c_int, [ctypes.POINTER(Config), ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p,
                                          ctypes.c_void_p]),
     "fdlbm_op_collide": (ctypes.c_int, [ctypes.POINTER(Config), ctypes.c_void_p, ctypes.POINTER(Fields)]),
+    "fdlbm_op_collision_terms": (ctypes.c_int, [ctypes.POINTER(Config), ctypes.c_void_p, ctypes.POINTER(Fields),
+                                                ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p]),
     "fdlbm_op_zou_he": (ctypes.c_int, [ctypes.POINTER(Config), ctypes.POINTER(Fields)]),
     "fdlbm_op_moments": (ctypes.c_int, [ctypes.POINTER(Config), ctypes.c_void_p, ctypes.POINTER(Fields)]),
 }

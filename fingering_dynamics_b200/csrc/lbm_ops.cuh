@@ -130,6 +130,37 @@ __global__ void __launch_bounds__(TPB) k_op_moments_local(const __grid_constant_
     out.mix_tau[c] = P.eta6m / (m.rho * D) + T(0.5);
 }
 
+// feq, geq and the forcing term of every direction, written to two lattices (src: feq|geq, dst: F|unused)
+template <typename T>
+__global__ void __launch_bounds__(TPB) k_op_terms(const __grid_constant__ LbmParams<T> P, FieldPtrs<T> in, const T *psi,
+                                                  T *eq_lat, T *force_lat)
+{
+    const int y = blockIdx.x * TPB + threadIdx.x, xl = blockIdx.y;
+    if (y >= P.H) return;
+    if (is_solid(P, xl, y)) return;
+    const size_t c = cell_idx(P.Hp, xl, y);
+    const T rho = in.rho[c], ux = in.ux[c], uy = in.uy[c], p = in.p[c], mu = in.mu[c], ps = psi[c];
+    const T pref = T(1) - T(0.5) / in.mix_tau[c];
+    const T Fx = mu * pref * in.gx[c], Fy = mu * pref * in.gy[c];
+    const T uF = ux * Fx + uy * Fy, usq15 = T(1.5) * (ux * ux + uy * uy);
+    const T w0 = T(4) / T(9), w1 = T(1) / T(9), w5 = T(1) / T(36), c0 = T(5) / T(3);
+    T *eq = eq_lat + lat_idx(P.Hp, xl, 0, y), *fo = force_lat + lat_idx(P.Hp, xl, 0, y);
+    eq[0] = rho - c0 * p - w0 * rho * usq15;
+    eq[(size_t)9 * P.Hp] = ps - c0 * P.gamma * mu - w0 * ps * usq15;
+    fo[0] = w0 * (T(-3) * uF);
+#pragma unroll
+    for (int i = 1; i < 9; ++i) {
+        const int ex = (i == 1 || i == 5 || i == 8) ? 1 : ((i == 3 || i == 6 || i == 7) ? -1 : 0);
+        const int ey = (i == 2 || i == 5 || i == 6) ? 1 : ((i == 4 || i == 7 || i == 8) ? -1 : 0);
+        const T w = i < 5 ? w1 : w5;
+        const T eu = T(ex) * ux + T(ey) * uy, eF = T(ex) * Fx + T(ey) * Fy;
+        const T poly = T(3) * eu + T(4.5) * eu * eu - usq15;
+        eq[(size_t)i * P.Hp] = w * (T(3) * p + rho * poly);
+        eq[(size_t)(9 + i) * P.Hp] = w * (T(3) * P.gamma * mu + ps * poly);
+        fo[(size_t)i * P.Hp] = w * (T(3) * (eF - uF) + T(9) * eu * eF);
+    }
+}
+
 }  // namespace fdlbm
 
 namespace {
@@ -264,6 +295,26 @@ int fdlbm_op_collide(const fdlbm_config *cfg, const uint8_t *solid, const fdlbm_
     k_collide_first<double><<<cell_grid(e, e->Wl), TPB, 0, e->stream>>>(P, field_ptrs<double>(e), (const double *)e->psi[0]);
     CU(cudaGetLastError());
     return download_pops(e, 0, io->f, io->g);
+}
+
+int fdlbm_op_collision_terms(const fdlbm_config *cfg, const uint8_t *solid, const fdlbm_fields *in, double *feq,
+                             double *geq, double *F)
+{
+    if (!cfg || !in) return fail(FDLBM_E_ARG, "null argument");
+    TempEngine t;
+    int rc = op_engine(t, cfg, 0, 0, false);
+    if (rc) return rc;
+    fdlbm_engine *e = t.e;
+    if ((rc = upload_solid(e, solid))) return rc;
+    if ((rc = fdlbm_set_state(e, 0, e->cfg.W, in))) return rc;
+    CU(cudaMemsetAsync(e->lat[0], 0, e->lat_elems() * e->esize, e->stream));
+    CU(cudaMemsetAsync(e->lat[1], 0, e->lat_elems() * e->esize, e->stream));
+    LbmParams<double> P = make_params<double>(e, 0, 0);
+    k_op_terms<double><<<cell_grid(e, e->Wl), TPB, 0, e->stream>>>(P, field_ptrs<double>(e), (const double *)e->psi[0],
+                                                                    (double *)e->lat[0], (double *)e->lat[1]);
+    CU(cudaGetLastError());
+    if ((rc = download_pops(e, 0, feq, geq))) return rc;
+    return download_pops(e, 1, F, nullptr);
 }
 
 int fdlbm_op_zou_he(const fdlbm_config *cfg, const fdlbm_fields *io)

@@ -1,0 +1,284 @@
+"""Shared machinery of the three drop-in drivers (fingering_periodic.py, fingering.py, validation.py):
+a Compute class with the reference's attribute and method names whose arithmetic runs on the GPU through
+the C ABI (include/fdlbm.h), plus run(), which keeps the whole time loop on the device.
+
+Conventions follow the reference: module-level constants (H, W, psi_wall, tau, ...) are read from the
+driver module AT CALL TIME (the reference's methods read globals, e.g. fingering_periodic.py:90,127,212),
+masked quantities are 1-D arrays over fluid cells in row-major order, f/g are (9,H,W), psi is (H,W).
+"""
+import ctypes
+import sys
+
+import numpy as np
+
+try:
+    from .. import _native as nat, geometry as geo, ops as _ops
+    from ..engine import Engine
+except ImportError:  # imported by bare name with this directory on sys.path
+    from fingering_dynamics_b200 import _native as nat, geometry as geo, ops as _ops
+    from fingering_dynamics_b200.engine import Engine
+
+W9 = np.array([4 / 9] + [1 / 9] * 4 + [1 / 36] * 4)
+E9 = np.array([[0, 0], [1, 0], [0, 1], [-1, 0], [0, -1], [1, 1], [-1, 1], [-1, -1], [1, -1]])
+
+
+class ComputeBase:
+    """VARIANT traits are set by the driver modules:
+    ZOU_HE 'fp' | 'fg' | 'none'; Y_WALL ghost rows = psi_wall; X_PERIODIC; A_SIGN (+1: mu = a psi (1-psi^2),
+    -1: validation.py's a psi (psi^2-1)); F3 outlet coefficient."""
+    ZOU_HE, Y_WALL, X_PERIODIC, A_SIGN, F3 = "fp", False, False, 1.0, 2 / 3
+
+    # -- module globals, read at call time --------------------------------------------------------
+    @property
+    def _m(self):
+        return sys.modules[type(self).__module__]
+
+    def _profiles(self):
+        m = self._m
+        H = m.H
+        if self.ZOU_HE == "fp":  # fingering_periodic.py:270-271
+            t = np.array([i * 3 / (H / 2) for i in range(int(-H / 2), int(H / 2))])
+            p = m.u0 * np.exp(-(t ** 2) / 2)
+            return p, p
+        if self.ZOU_HE == "fg":  # fingering.py:299,370
+            p = np.full(H, float(m.u0))
+            return p, p
+        return None, None
+
+    def _engine_kwargs(self):
+        m = self._m
+        inlet, outlet = self._profiles()
+        return dict(tau=m.tau, gamma=self.gamma, a=self.A_SIGN * m.a, kappa=m.kappa, Eta_n=m.Eta_n, M=m.M,
+                    psi_wall=m.psi_wall, psi_y_wall=self.Y_WALL, x_periodic=self.X_PERIODIC, zou_he=self.ZOU_HE,
+                    inlet_ux=inlet, outlet_ux=outlet, outlet_f3_coef=self.F3)
+
+    def _cfg(self):
+        m = self._m
+        kw = self._engine_kwargs()
+        c = nat.Config()
+        c.H, c.W = m.H, m.W
+        c.psi_y_wall, c.x_periodic = int(kw["psi_y_wall"]), int(kw["x_periodic"])
+        c.zou_he = {"none": 0, "fp": 1, "fg": 2}[kw["zou_he"]]
+        c.x0, c.x1 = 0, m.W
+        for k in ("tau", "gamma", "a", "kappa", "Eta_n", "M", "psi_wall", "outlet_f3_coef"):
+            setattr(c, k, float(kw[k]))
+        c.psi_left, c.psi_right = 1.0, -1.0
+        self._keep = [None if kw[k] is None else np.ascontiguousarray(kw[k], dtype=np.float64) for k in ("inlet_ux", "outlet_ux")]
+        if self._keep[0] is not None:
+            c.inlet_ux, c.outlet_ux = self._keep[0].ctypes.data, self._keep[1].ctypes.data
+        return c
+
+    # -- masked <-> full ----------------------------------------------------------------------------
+    def _full(self, v):
+        m = self._m
+        v = np.asarray(v, dtype=np.float64)
+        if v.shape == (m.H, m.W):
+            return np.ascontiguousarray(v)
+        out = np.zeros((m.H, m.W))
+        out[self.mask] = v
+        return out
+
+    def _masked(self, a):
+        return a if self._full_grid else a[self.mask]
+
+    def _fields(self, **extra):
+        """fdlbm_fields over the current attributes (full-grid copies kept alive in self._hold)"""
+        names = ("f", "g", "psi", "rho", "ux", "uy", "p", "mu", "mix_tau", "nabla_psix", "nabla_psiy", "nabla_psi2")
+        hold = {}
+        F = nat.Fields()
+        for k in names:
+            v = extra.get(k, getattr(self, k, None))
+            if v is None:
+                continue
+            a = nat.as_f64(v) if k in ("f", "g") else self._full(v)
+            if k == "mix_tau":
+                a = np.where(self.mask, a, 1.0)
+            a = np.ascontiguousarray(a)
+            hold[k] = a
+            setattr(F, k, a.ctypes.data)
+        self._hold = hold
+        return F, hold
+
+    @property
+    def _solid(self):
+        return np.ascontiguousarray(~self.mask, dtype=np.uint8)
+
+    # -- device operators -----------------------------------------------------------------------------
+    def _stencils(self):
+        m = self._m
+        psi = np.array(self.psi, dtype=np.float64)
+        if not self._full_grid:
+            psi[self.block_mask] = m.psi_wall  # fingering_periodic.py:216-217
+        psi = np.ascontiguousarray(psi)
+        gx, gy, lap = (np.empty((m.H, m.W)) for _ in range(3))
+        c = self._cfg()
+        nat.check(nat.lib().fdlbm_op_stencils(ctypes.byref(c), nat.ptr(psi), nat.ptr(gx), nat.ptr(gy), nat.ptr(lap)))
+        return gx, gy, lap
+
+    def getNabla_psix(self):
+        return self._stencils()[0]
+
+    def getNabla_psiy(self):
+        return self._stencils()[1]
+
+    def getNabla_psi2(self):
+        return self._stencils()[2]
+
+    def _moments(self):
+        """fdlbm_op_moments on the current f, g: everything fingering_periodic.py:470-479 computes"""
+        m = self._m
+        out = {k: np.zeros((m.H, m.W)) for k in ("psi", "rho", "ux", "uy", "p", "mu", "mix_tau", "nabla_psix",
+                                                  "nabla_psiy", "nabla_psi2")}
+        F = nat.Fields()
+        f, g = nat.as_f64(self.f), nat.as_f64(self.g)
+        F.f, F.g = f.ctypes.data, g.ctypes.data
+        for k, a in out.items():
+            setattr(F, k, a.ctypes.data)
+        c = self._cfg()
+        nat.check(nat.lib().fdlbm_op_moments(ctypes.byref(c), nat.ptr(self._solid), ctypes.byref(F)))
+        return out
+
+    def getRho(self):
+        return self._masked(self._moments()["rho"])
+
+    def udpatePsi(self):
+        self.psi = self._moments()["psi"]
+
+    updatePsi = udpatePsi
+
+    def _terms(self):
+        m = self._m
+        F, hold = self._fields()
+        feq, geq, Fo = (np.zeros((9, m.H, m.W)) for _ in range(3))
+        c = self._cfg()
+        nat.check(nat.lib().fdlbm_op_collision_terms(ctypes.byref(c), nat.ptr(self._solid), ctypes.byref(F), nat.ptr(feq),
+                                                     nat.ptr(geq), nat.ptr(Fo)))
+        return feq, geq, Fo
+
+    def getfeq(self, n):
+        return self._masked(self._terms()[0][n])
+
+    def getgeq(self, n):
+        return self._masked(self._terms()[1][n])
+
+    def getLarge_F(self, n):
+        return self._masked(self._terms()[2][n])
+
+    def _collided(self):
+        F, hold = self._fields()
+        f, g = hold["f"].copy(), hold["g"].copy()
+        F.f, F.g = f.ctypes.data, g.ctypes.data
+        c = self._cfg()
+        nat.check(nat.lib().fdlbm_op_collide(ctypes.byref(c), nat.ptr(self._solid), ctypes.byref(F)))
+        return f, g
+
+    def getF(self, i):
+        """post-collision f_i on fluid cells (fingering_periodic.py:258-260), from the current macroscopic arrays"""
+        return self._masked(self._collided()[0][i])
+
+    def getG(self, i):
+        return self._masked(self._collided()[1][i])
+
+    def _zou_he(self):
+        F, hold = self._fields()
+        f, g = hold["f"].copy(), hold["g"].copy()
+        F.f, F.g = f.ctypes.data, g.ctypes.data
+        c = self._cfg()
+        nat.check(nat.lib().fdlbm_op_zou_he(ctypes.byref(c), ctypes.byref(F)))
+        return f, g
+
+    def zou_he_boundary_inlet(self):
+        f, g = self._zou_he()
+        self.f[:, :, 0], self.g[:, :, 0] = f[:, :, 0], g[:, :, 0]
+
+    def zou_he_boundary_outlet(self):
+        f, g = self._zou_he()
+        self.f[:, :, -1], self.g[:, :, -1] = f[:, :, -1], g[:, :, -1]
+
+    # -- simple algebra on stored arrays (the reference's one-liners) ------------------------------------
+    def getP(self):
+        return 1 / 3 * self.rho + self._masked(np.asarray(self.psi)) * self.mu
+
+    def getMu_plain(self):
+        m = self._m
+        return m.a * self.psi * (1.0 - self.psi ** 2) * self.A_SIGN - m.kappa * self.nabla_psi2
+
+    def getMu(self):
+        return self._masked(self.getMu_plain())
+
+    def getUx(self):
+        return self._masked(self._moments()["ux"])
+
+    def getUy(self):
+        return self._masked(self._moments()["uy"])
+
+    def getMix_tau(self):
+        m = self._m
+        v1 = m.Eta_n / self.rho
+        v2 = m.Eta_n * m.M / self.rho
+        psi = self._masked(np.asarray(self.psi))
+        return 3 * (2 * v1 * v2 / (v1 * (1.0 - psi) + v2 * (1.0 + psi))) + 0.5
+
+    def getA0(self):
+        return (self.rho - 3.0 * (1.0 - self.w[0]) * self.p) / self.w[0]
+
+    def getA1_8(self):
+        return 3 * self.p
+
+    def getB0(self):
+        return (self._masked(np.asarray(self.psi)) - 3.0 * (1.0 - self.w[0]) * self.gamma * self.mu) / self.w[0]
+
+    def getB1_8(self):
+        return 3 * self.gamma * self.mu
+
+    # -- the whole loop on the device ----------------------------------------------------------------------
+    def make_engine(self, reflect, dtype="f64", **kw):
+        m = self._m
+        e = Engine(m.H, m.W, dtype=dtype, **self._engine_kwargs(), **kw)
+        e.set_geometry(self._solid, reflect)
+        F, hold = self._fields()
+        e.set_state(**{k: v for k, v in hold.items()})
+        return e
+
+    def pull_from(self, engine):
+        """refresh every attribute from the engine (what the reference holds after the iterations done)"""
+        st = engine.get_state(("f", "g", "psi", "rho", "ux", "uy", "p", "mu", "mix_tau", "nabla_psix", "nabla_psiy",
+                               "nabla_psi2"))
+        self.f, self.g, self.psi = st["f"], st["g"], st["psi"]
+        for k in ("rho", "ux", "uy", "p", "mu", "mix_tau"):
+            setattr(self, k, self._masked(st[k]))
+        self.nabla_psix, self.nabla_psiy, self.nabla_psi2 = st["nabla_psix"], st["nabla_psiy"], st["nabla_psi2"]
+
+
+def stream(f, g):
+    """stream(f, g) of the reference drivers (fingering_periodic.py:327-343): in place, all cells, periodic."""
+    _ops.stream(f, g)
+
+
+def wall_rows(f_behind, g_behind, f, g):
+    """bottom_top_wall / halfway_bounceback of the drivers (fingering_periodic.py:354-366, fingering.py:432-451,
+    validation.py:357-376): row 0 reflects {2,5,6} and row -1 reflects {4,7,8} of the arrays AS PASSED
+    (fingering.py:573 passes the [:, 1:-1] row slices, so rows 1 and H-2 of the grid are hit)."""
+    _, H, W = f.shape
+    _ops.bounce_back(geo.reflect_bits_wall_rows(H, W, 0, H - 1), f_behind, g_behind, f, g)
+
+
+def run_loop(cm, reflect, n_steps, frames_every=0, dtype="f64"):
+    """Advance `cm` n_steps reference iterations on the GPU; returns the list of psi frames taken every
+    `frames_every` steps BEFORE the step, like fingering.py:565-566 (empty if 0)."""
+    eng = cm.make_engine(reflect, dtype=dtype)
+    frames = []
+    done = 0
+    try:
+        if frames_every:
+            while done < n_steps:
+                frames.append(eng.get_state(("psi",))["psi"])
+                k = min(frames_every, n_steps - done)
+                eng.step(k)
+                done += k
+        else:
+            eng.step(n_steps)
+        cm.pull_from(eng)
+    finally:
+        eng.close()
+    return frames

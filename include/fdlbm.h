@@ -137,6 +137,10 @@ int fdlbm_op_bounce_back(int H, int W, const uint8_t *reflect, const double *f_b
 int fdlbm_op_stencils(const fdlbm_config *cfg, const double *psi, double *gx, double *gy, double *lap);
 /* the collision of one iteration on fluid cells (fingering_periodic.py:455-460), in place on f, g */
 int fdlbm_op_collide(const fdlbm_config *cfg, const uint8_t *solid, const fdlbm_fields *io);
+/* Compute.getfeq / getgeq / getLarge_F for all nine directions (fingering_periodic.py:171-199) from the
+ * macroscopic arrays in `in`; feq, geq, F are (9,H,W) outputs (zero on solid cells), any may be NULL */
+int fdlbm_op_collision_terms(const fdlbm_config *cfg, const uint8_t *solid, const fdlbm_fields *in, double *feq,
+                             double *geq, double *F);
 /* zou_he_boundary_inlet + _outlet (fingering_periodic.py:268-324 / fingering.py:298-390), in place */
 int fdlbm_op_zou_he(const fdlbm_config *cfg, const fdlbm_fields *io);
 /* the moment updates of one iteration (fingering_periodic.py:470-479): f,g in; all fields out */

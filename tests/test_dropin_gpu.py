@@ -1,0 +1,125 @@
+"""The drop-in twins of the reference modules (fingering_dynamics_b200/lattice_boltzmann/*.py) against the
+reference's own outputs: same module-level names, NumPy in / NumPy out, loop on the GPU."""
+import numpy as np
+import pytest
+
+from tests import helpers as hp
+
+pytestmark = pytest.mark.gpu
+TOL = 1e-10
+
+
+def _masked_full(mask, v):
+    out = np.zeros(mask.shape)
+    out[mask] = v
+    return out
+
+
+def _check_compute(cm, d, tag, mask, tol=TOL, skip=()):
+    for k in ("f", "g", "psi", "nabla_psix", "nabla_psiy", "nabla_psi2"):
+        if k in skip or "%s_%s" % (tag, k) not in d:
+            continue
+        assert hp.rel_err(getattr(cm, k), d["%s_%s" % (tag, k)]) <= tol, (tag, k)
+    for k in ("rho", "ux", "uy", "p", "mu", "mix_tau"):
+        if k in skip:
+            continue
+        v = getattr(cm, k)
+        v = _masked_full(mask, v) if v.ndim == 1 else v
+        assert hp.rel_err(v, d["%s_%s" % (tag, k)]) <= tol, (tag, k)
+
+
+def test_fingering_periodic_twin(golden, monkeypatch):
+    from fingering_dynamics_b200.lattice_boltzmann import fingering_periodic as FP, _compute
+    from fingering_dynamics_b200.lattice_boltzmann.create_block import Createblock
+    from fingering_dynamics_b200 import geometry as geo
+    d = golden("fp_small")
+    monkeypatch.setattr(FP, "H", int(d["H"]))
+    monkeypatch.setattr(FP, "W", int(d["W"]))
+    circles = [((int(c[0]), int(c[1])), int(c[2])) for c in d["circles"]]
+    bpa, side, cave, vex = Createblock(FP.H, FP.W).setCirleblock(circles)
+    mask = np.logical_not(bpa == 1)
+    assert np.array_equal(mask, d["mask"])
+    cm = FP.Compute(mask)
+    _check_compute(cm, d, "s0", mask, tol=1e-14)
+    assert cm.rho.shape == (int(mask.sum()),) and cm.feq.shape == (9, int(mask.sum()))
+    # fine-grained getters are consistent with the collision (fingering_periodic.py:258-260)
+    i = 5
+    want = cm.f[i][mask] - 1.0 / cm.mix_tau * (cm.f[i][mask] - cm.getfeq(i)) + cm.getLarge_F(i)
+    assert hp.rel_err(cm.getF(i), want) <= 1e-14
+    _compute.run_loop(cm, geo.reflect_bits_circle(side, cave, vex), 10)
+    _check_compute(cm, d, "s10", mask)
+
+
+def test_fingering_twin_with_seeded_rng(golden, monkeypatch):
+    from fingering_dynamics_b200.lattice_boltzmann import fingering as FG, _compute
+    from fingering_dynamics_b200.lattice_boltzmann.create_block import Createblock
+    d = golden("fg_small")
+    monkeypatch.setattr(FG, "H", int(d["H"]))
+    monkeypatch.setattr(FG, "W", int(d["W"]))
+    rects = [((int(r[0]), int(r[1])), (int(r[2]), int(r[3]))) for r in d["rects"]]
+    bpa, corner_list = Createblock(FG.H, FG.W).setblock(rects)
+    mask = np.logical_not(bpa == 1)
+    assert np.array_equal(mask, d["mask"])
+    np.random.seed(7)  # the seed tests/golden/make_golden.py used before the reference's Compute(mask)
+    cm = FG.Compute(mask)
+    assert np.array_equal(_masked_full(mask, cm.rho), d["s0_rho"])  # same two RNG draws as fingering.py:106-107
+    _check_compute(cm, d, "s0", mask, tol=1e-13)
+    frames = _compute.run_loop(cm, FG.reflect_bits(corner_list), 10, frames_every=4)
+    _check_compute(cm, d, "s10", mask)
+    assert len(frames) == 3 and np.array_equal(frames[0], d["s0_psi"])
+
+
+@pytest.mark.parametrize("name,wall", [("va_small", 0.0), ("va_small_wet", 0.3)])
+def test_validation_twin(golden, monkeypatch, name, wall):
+    from fingering_dynamics_b200.lattice_boltzmann import validation as VA, _compute
+    from fingering_dynamics_b200 import geometry as geo
+    d = golden(name)
+    monkeypatch.setattr(VA, "H", int(d["H"]))
+    monkeypatch.setattr(VA, "W", int(d["W"]))
+    monkeypatch.setattr(VA, "psi_wall", wall)
+    cm = VA.Compute()
+    mask = np.ones((VA.H, VA.W), dtype=bool)
+    _check_compute(cm, d, "s0", mask, tol=1e-13)
+    assert hp.rel_err(cm.e, d["e"]) <= 1e-15
+    _compute.run_loop(cm, geo.reflect_bits_wall_rows(VA.H, VA.W, 0, VA.H - 1), 10)
+    _check_compute(cm, d, "s10", mask, skip=("mix_tau",))
+
+
+def test_module_level_functions(golden):
+    """stream, bottom_top_wall on row-slice views (fingering.py:573), Bounce_back.* -- in place, like the reference"""
+    from fingering_dynamics_b200.lattice_boltzmann import fingering as FG, validation as VA
+    from fingering_dynamics_b200.lattice_boltzmann.bounce_back import Bounce_back
+    d = golden("ops")
+    H, W = int(d["H"]), int(d["W"])
+    f, g = d["f_in"].copy(), d["g_in"].copy()
+    FG.stream(f, g)
+    assert np.array_equal(f, d["f_stream"]) and np.array_equal(g, d["g_stream"])
+    bb = Bounce_back(H, W)
+    side = [d["circ_side_%d" % k] for k in range(4)]
+    cave = [d["circ_concave_%d" % k] for k in range(4)]
+    vex = [d["circ_convex_%d" % k] for k in range(4)]
+    f, g = d["f_stream"].copy(), d["g_stream"].copy()
+    bb.halfway_bounceback_circle(side, cave, vex, d["f_in"], d["g_in"], f, g)
+    assert np.array_equal(f, d["f_bb_circle"]) and np.array_equal(g, d["g_bb_circle"])
+    f, g = d["f_stream"].copy(), d["g_stream"].copy()
+    bb.halfway_bounceback_rec(hp.corner_dicts(d["rect_corners"]), d["f_in"], d["g_in"], f, g)
+    assert np.array_equal(f, d["f_bb_rect"]) and np.array_equal(g, d["g_bb_rect"])
+    FG.bottom_top_wall(d["f_in"][:, 1:-1], d["g_in"][:, 1:-1], f[:, 1:-1], g[:, 1:-1])
+    assert np.array_equal(f, d["f_bb_rect_walls"]) and np.array_equal(g, d["g_bb_rect_walls"])
+    f, g = d["f_stream"].copy(), d["g_stream"].copy()
+    VA.halfway_bounceback(d["f_in"], d["g_in"], f, g)
+    assert np.array_equal(f, d["f_bb_va"]) and np.array_equal(g, d["g_bb_va"])
+    f, g = d["f_stream"].copy(), d["g_stream"].copy()
+    bb.left_boundary(d["f_in"], d["g_in"], f, g, 3)
+    assert np.array_equal(f, d["f_left_boundary"]) and np.array_equal(g, d["g_left_boundary"])
+
+
+def test_fingering_periodic_main_default_geometry(golden):
+    """main() of the twin on the shipped configuration (400x400, 90 circles) for 100 steps against the
+    reference's own scalars (tests/golden/make_golden.py --full)."""
+    from fingering_dynamics_b200.lattice_boltzmann import fingering_periodic as FP
+    d = golden("fp_full_scalars")
+    cm = FP.main(max_t=100, show=False)
+    assert abs(cm.psi.sum() - float(d["s100_sum_psi"])) <= 1e-10 * abs(float(d["s100_sum_psi"]))
+    assert abs(cm.rho.sum() - float(d["s100_sum_rho"])) <= 1e-10 * float(d["s100_sum_rho"])
+    assert hp.rel_err(cm.psi[::5, ::5], d["s100_psi_sub"]) <= TOL
