@@ -34,7 +34,7 @@ def test_fused_equals_twopass_at_8192x2048():
         e.close()
     for k in res["fused"]:
         assert np.array_equal(res["fused"][k], res["twopass"][k]), k
-    assert np.isfinite(res["fused"]["psi"]).all() and res["fused"]["rho"][solid == 0].min() > 0.9
+    assert np.isfinite(res["fused"]["psi"]).all() and res["fused"]["rho"][solid == 0].min() > 0.5
 
 
 @pytest.mark.parametrize("dtype", ["f64", "f32"])
