@@ -28,7 +28,7 @@ namespace fdlbm {
 #define FDLBM_FUSED_TY 128
 #endif
 #ifndef FDLBM_FUSED_D
-#define FDLBM_FUSED_D 2
+#define FDLBM_FUSED_D 1  // NS = 3 + D = 4 stages: a power of two, the slot of a column is c & 3
 #endif
 // resident CTAs per SM the register allocation is bounded for: fp64 needs ~166 registers to stay free of
 // spills (3 CTAs = 12 warps, 48 KB of stages each); fp32 fits 128 registers (4 CTAs)
@@ -166,7 +166,7 @@ __global__ void __launch_bounds__(TY, sizeof(T) == 8 ? FDLBM_FUSED_MINB64 : FDLB
     const int ye1 = wrap_row(edge_lo ? y - 1 : y + 1), je1 = edge_lo ? j - 1 : j + 1;
     const int ye2 = wrap_row(y + 1), je2 = j + 1;  // second neighbour of a one-row warp (edge2)
 
-    auto slot = [](int c) { return ((c % NS) + NS) % NS; };
+    auto slot = [](int c) { return (NS & (NS - 1)) == 0 ? (c & (NS - 1)) : ((c % NS) + NS) % NS; };
     auto in_domain = [&](int c) { return P.x_periodic || (P.gx0 + c >= 0 && P.gx0 + c < P.W); };
 
     // one pipeline step: g column v+2+D (and f column v+1+D when staged); only columns this run reads
