@@ -172,6 +172,11 @@ def main():
     solid, refl = syn.porous_geometry(H, W, col0=max(0, x0 - 2), ncols=min(W, x1 + 2) - max(0, x0 - 2))
     own = slice(x0 - max(0, x0 - 2), x0 - max(0, x0 - 2) + (x1 - x0))
     st = syn.fp_initial_state(np.ascontiguousarray(solid[:, own]), c, col0=x0, alloc=pinned_empty)
+    for k in list(st):  # every array of the e2e job lives in page-locked host memory
+        if k not in ("f", "g"):
+            pin = pinned_empty(st[k].shape)
+            pin[...] = st[k]
+            st[k] = pin
 
     eng = Engine(H, W, tau=c["tau"], gamma=c["gamma"], a=c["a"], kappa=c["kappa"], Eta_n=c["Eta_n"], M=c["M"],
                  psi_wall=c["psi_wall"], zou_he="fp", inlet_ux=c["inlet_ux"], outlet_ux=c["outlet_ux"], dtype=args.dtype,

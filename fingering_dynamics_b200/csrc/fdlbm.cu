@@ -53,6 +53,10 @@ struct fdlbm_engine {
     void *staging = nullptr;
     size_t staging_bytes = 0;
     cudaStream_t stream = nullptr;
+    cudaStream_t copy_stream = nullptr;                       // host<->device transfers of set_state / get_state
+    cudaEvent_t stage_full[2] = {nullptr, nullptr};           // staging buffer b holds a produced plane
+    cudaEvent_t stage_free[2] = {nullptr, nullptr};           // ... and has been consumed
+    uint64_t stage_seq = 0;
     int cur = 0, pcur = 0;
     int state = ST_EMPTY;
     bool have_geometry = false;
@@ -123,6 +127,8 @@ FieldPtrs<T> field_ptrs(const fdlbm_engine *e)
 int ensure_staging(fdlbm_engine *e, size_t bytes)
 {
     if (bytes <= e->staging_bytes) return 0;
+    if (e->copy_stream) CU(cudaStreamSynchronize(e->copy_stream));
+    CU(cudaStreamSynchronize(e->stream));
     if (e->staging) cudaFree(e->staging);
     e->staging = nullptr;
     e->staging_bytes = 0;
@@ -216,24 +222,35 @@ template <typename T>
 int upload_planes(fdlbm_engine *e, const double *host, int nplanes, int col0, int ncw, T *base, size_t plane_stride,
                   size_t xstride)
 {
+    // Plane by plane through two staging buffers: the host->device copy of plane k+1 (copy stream) runs
+    // while plane k is transposed into the device layout (engine stream); events order the reuse.
     const Overlap ov = overlap(e, col0, ncw);
     if (!ov.n) return 0;
     const int H = e->cfg.H;
-    int rc = ensure_staging(e, (size_t)nplanes * H * ov.n * sizeof(double));
+    const size_t plane_bytes = (size_t)H * ov.n * sizeof(double);
+    int rc = ensure_staging(e, 2 * plane_bytes);
     if (rc) return rc;
-    CU(cudaMemcpy2DAsync(e->staging, (size_t)ov.n * sizeof(double), host + (ov.lo - col0), (size_t)ncw * sizeof(double),
-                         (size_t)ov.n * sizeof(double), (size_t)nplanes * H, cudaMemcpyHostToDevice, e->stream));
     const int xl_lo = ov.lo - e->cfg.x0, xl_hi = xl_lo + ov.n;
     dim3 grid((ov.n + 31) / 32, (H + 31) / 32), block(32, 8);
     for (int k = 0; k < nplanes; ++k) {
-        k_transpose_in<double, T><<<grid, block, 0, e->stream>>>((const double *)e->staging + (size_t)k * H * ov.n, H, ov.n,
-                                                                  ov.lo, base + k * plane_stride, xstride, xl_lo, xl_hi,
-                                                                  e->cfg.x0, e->cfg.W, 0);
+        const int b = (int)(e->stage_seq & 1);
+        char *st = (char *)e->staging + (size_t)b * plane_bytes;
+        const double *src = host + (size_t)k * H * ncw + (ov.lo - col0);
+        CU(cudaStreamWaitEvent(e->copy_stream, e->stage_free[b], 0));  // the transpose that last read this buffer
+        if (ov.n == ncw)
+            CU(cudaMemcpyAsync(st, src, plane_bytes, cudaMemcpyHostToDevice, e->copy_stream));
+        else
+            CU(cudaMemcpy2DAsync(st, (size_t)ov.n * sizeof(double), src, (size_t)ncw * sizeof(double),
+                                 (size_t)ov.n * sizeof(double), (size_t)H, cudaMemcpyHostToDevice, e->copy_stream));
+        CU(cudaEventRecord(e->stage_full[b], e->copy_stream));
+        CU(cudaStreamWaitEvent(e->stream, e->stage_full[b], 0));
+        k_transpose_in<double, T><<<grid, block, 0, e->stream>>>((const double *)st, H, ov.n, ov.lo, base + k * plane_stride,
+                                                                  xstride, xl_lo, xl_hi, e->cfg.x0, e->cfg.W, 0);
+        CU(cudaEventRecord(e->stage_free[b], e->stream));
         e->launches += 1;
+        e->stage_seq += 1;
     }
     CU(cudaGetLastError());
-    // the staging buffer is reused by the next upload: serialise
-    CU(cudaStreamSynchronize(e->stream));
     return 0;
 }
 
@@ -245,19 +262,37 @@ int download_planes(fdlbm_engine *e, double *host, int nplanes, int col0, int nc
     const Overlap ov = overlap(e, col0, ncw);
     if (!ov.n) return 0;
     const int H = e->cfg.H;
-    int rc = ensure_staging(e, (size_t)nplanes * H * ov.n * sizeof(double));
+    const size_t plane_bytes = (size_t)H * ov.n * sizeof(double);
+    int rc = ensure_staging(e, 2 * plane_bytes);
     if (rc) return rc;
     const int xl_lo = ov.lo - e->cfg.x0, xl_hi = xl_lo + ov.n;
     dim3 grid((ov.n + 31) / 32, (H + 31) / 32), block(32, 8);
-    for (int k = 0; k < nplanes; ++k) {
+    for (int k = 0; k < nplanes; ++k) {  // transpose of plane k+1 (engine stream) overlaps the D2H copy of plane k
+        const int b = (int)(e->stage_seq & 1);
+        char *st = (char *)e->staging + (size_t)b * plane_bytes;
+        double *dst = host + (size_t)k * H * ncw + (ov.lo - col0);
+        CU(cudaStreamWaitEvent(e->stream, e->stage_free[b], 0));
         k_transpose_out<T, double><<<grid, block, 0, e->stream>>>(base + k * plane_stride, xstride, xl_lo, xl_hi, e->cfg.x0,
-                                                                   (double *)e->staging + (size_t)k * H * ov.n, H, ov.n,
-                                                                   ov.lo);
+                                                                   (double *)st, H, ov.n, ov.lo);
+        CU(cudaEventRecord(e->stage_full[b], e->stream));
+        CU(cudaStreamWaitEvent(e->copy_stream, e->stage_full[b], 0));
+        if (ov.n == ncw)
+            CU(cudaMemcpyAsync(dst, st, plane_bytes, cudaMemcpyDeviceToHost, e->copy_stream));
+        else
+            CU(cudaMemcpy2DAsync(dst, (size_t)ncw * sizeof(double), st, (size_t)ov.n * sizeof(double),
+                                 (size_t)ov.n * sizeof(double), (size_t)H, cudaMemcpyDeviceToHost, e->copy_stream));
+        CU(cudaEventRecord(e->stage_free[b], e->copy_stream));
         e->launches += 1;
+        e->stage_seq += 1;
     }
     CU(cudaGetLastError());
-    CU(cudaMemcpy2DAsync(host + (ov.lo - col0), (size_t)ncw * sizeof(double), e->staging, (size_t)ov.n * sizeof(double),
-                         (size_t)ov.n * sizeof(double), (size_t)nplanes * H, cudaMemcpyDeviceToHost, e->stream));
+    return 0;
+}
+
+// host buffers are borrowed for the duration of an API call: wait for every queued transfer
+int drain_transfers(fdlbm_engine *e)
+{
+    CU(cudaStreamSynchronize(e->copy_stream));
     CU(cudaStreamSynchronize(e->stream));
     return 0;
 }
@@ -285,7 +320,7 @@ int set_state_t(fdlbm_engine *e, int col0, int ncw, const fdlbm_fields *in)
     }
     e->state = ST_PRE;
     e->iters = 0;
-    return 0;
+    return drain_transfers(e);
 }
 
 template <typename T>
@@ -311,7 +346,7 @@ int get_state_t(fdlbm_engine *e, int col0, int ncw, const fdlbm_fields *out)
                        out->nabla_psi2};
     for (int k = 0; k < 9; ++k)
         if ((rc = download_planes<T>(e, dsts[k], 1, col0, ncw, fb + k * n, 0, Hp))) return rc;
-    return 0;
+    return drain_transfers(e);
 }
 
 int upload_profile(fdlbm_engine *e, const double *host, void **dev)
@@ -388,6 +423,11 @@ int fdlbm_create(const fdlbm_config *cfg, fdlbm_engine **out)
         }                                                                                             \
     } while (0)
     CUE(cudaStreamCreateWithFlags(&e->stream, cudaStreamNonBlocking));
+    CUE(cudaStreamCreateWithFlags(&e->copy_stream, cudaStreamNonBlocking));
+    for (int k = 0; k < 2; ++k) {
+        CUE(cudaEventCreateWithFlags(&e->stage_full[k], cudaEventDisableTiming));
+        CUE(cudaEventCreateWithFlags(&e->stage_free[k], cudaEventDisableTiming));
+    }
     for (int k = 0; k < 2; ++k) {
         CUE(cudaMalloc(&e->lat[k], e->lat_elems() * e->esize));
         CUE(cudaMemsetAsync(e->lat[k], 0, e->lat_elems() * e->esize, e->stream));
@@ -422,12 +462,18 @@ void fdlbm_destroy(fdlbm_engine *e)
 {
     if (!e) return;
     cudaSetDevice(e->cfg.device);
+    if (e->copy_stream) cudaStreamSynchronize(e->copy_stream);
     if (e->stream) cudaStreamSynchronize(e->stream);
     void *ptrs[] = {e->lat[0], e->lat[1], e->psi[0], e->psi[1], e->fields, e->reflect, e->solid_bytes,
                     e->solid, e->inlet, e->outlet, e->staging};
     for (void *p : ptrs)
         if (p) cudaFree(p);
     if (e->stream) cudaStreamDestroy(e->stream);
+    if (e->copy_stream) cudaStreamDestroy(e->copy_stream);
+    for (int k = 0; k < 2; ++k) {
+        if (e->stage_full[k]) cudaEventDestroy(e->stage_full[k]);
+        if (e->stage_free[k]) cudaEventDestroy(e->stage_free[k]);
+    }
     delete e;
 }
 

@@ -210,7 +210,8 @@ int download_pops(fdlbm_engine *e, int which, double *f, double *g)
     const size_t Hp = e->Hp;
     int rc = download_planes<double>(e, f, 9, 0, e->cfg.W, lat, Hp, (size_t)NPOP * Hp);
     if (rc) return rc;
-    return download_planes<double>(e, g, 9, 0, e->cfg.W, lat + 9 * Hp, Hp, (size_t)NPOP * Hp);
+    if ((rc = download_planes<double>(e, g, 9, 0, e->cfg.W, lat + 9 * Hp, Hp, (size_t)NPOP * Hp))) return rc;
+    return drain_transfers(e);
 }
 
 int upload_solid(fdlbm_engine *e, const uint8_t *solid)
@@ -279,7 +280,8 @@ int fdlbm_op_stencils(const fdlbm_config *cfg, const double *psi, double *gx, do
     CU(cudaGetLastError());
     if ((rc = download_planes<double>(e, gx, 1, 0, e->cfg.W, F.gx, 0, e->Hp))) return rc;
     if ((rc = download_planes<double>(e, gy, 1, 0, e->cfg.W, F.gy, 0, e->Hp))) return rc;
-    return download_planes<double>(e, lap, 1, 0, e->cfg.W, F.lap, 0, e->Hp);
+    if ((rc = download_planes<double>(e, lap, 1, 0, e->cfg.W, F.lap, 0, e->Hp))) return rc;
+    return drain_transfers(e);
 }
 
 int fdlbm_op_collide(const fdlbm_config *cfg, const uint8_t *solid, const fdlbm_fields *io)
@@ -362,7 +364,7 @@ int fdlbm_op_moments(const fdlbm_config *cfg, const uint8_t *solid, const fdlbm_
     double *srcs[9] = {F.rho, F.ux, F.uy, F.p, F.mu, F.mix_tau, F.gx, F.gy, F.lap};
     for (int k = 0; k < 9; ++k)
         if ((rc = download_planes<double>(e, dsts[k], 1, 0, W, srcs[k], 0, Hp))) return rc;
-    return 0;
+    return drain_transfers(e);
 }
 
 }  // extern "C"
