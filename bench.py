@@ -144,6 +144,7 @@ def main():
     ap.add_argument("--kernel", default="auto", choices=["auto", "fused", "twopass"])
     ap.add_argument("--H", type=int, default=H_DEFAULT)
     ap.add_argument("--W", type=int, default=0, help="global columns (default 8192 per GPU)")
+    ap.add_argument("--halo", default="peer", choices=["peer", "nccl"], help="slab halo transport for N>1")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--no-e2e", action="store_true")
     args = ap.parse_args()
@@ -182,7 +183,7 @@ def main():
                  psi_wall=c["psi_wall"], zou_he="fp", inlet_ux=c["inlet_ux"], outlet_ux=c["outlet_ux"], dtype=args.dtype,
                  kernel=args.kernel, device=local, slab=(x0, x1), external_halo=world > 1)
     eng.set_geometry(solid, refl, col0=max(0, x0 - 2))
-    runner = SlabRunner(eng, rank, world)
+    runner = SlabRunner(eng, rank, world, halo=args.halo)
     stream = torch.cuda.ExternalStream(eng.stream, device=torch.device("cuda", local))
 
     def barrier():
@@ -192,7 +193,7 @@ def main():
         eng.sync()
 
     # ---- device-resident throughput ("value") -------------------------------------------------------
-    eng.set_state(col0=x0, **st)
+    runner.set_state(col0=x0, **st)
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     with ClockSampler(local) as clocks:   # nvidia-smi needs a moment to start: launch it before the warm-up
         runner.step(Wm)
@@ -220,7 +221,7 @@ def main():
         d2h = sum(v.nbytes for v in out.values())
         barrier()
         t0 = time.perf_counter()
-        eng.set_state(col0=x0, **st)        # H2D of f, g and the macroscopic arrays (pinned host memory)
+        runner.set_state(col0=x0, **st)     # H2D of f, g and the macroscopic arrays (pinned host memory)
         runner.step(K)
         runner.get_state(("psi", "rho", "ux", "uy"), out=out)   # D2H of the result fields
         barrier()
@@ -257,7 +258,9 @@ def main():
                        "obstacles": "circles r 8-12 on a jittered 40-pitch lattice, seed 1234",
                        "kernel": args.kernel, "l2": "state (%.1f GB per lattice copy) far exceeds the 126 MB L2; no flush needed"
                                                     % (cells_local * 18 * (8 if args.dtype == "f64" else 4) / 1e9),
-                       "parallelism": "slab%d" % world},
+                       "parallelism": "slab%d" % world,
+                       "halo": ("in-kernel peer stores over NVLink + stream flags" if args.halo == "peer" else "NCCL send/recv")
+                       if world > 1 else "none"},
             "clocks": clocks.summary(), "gpu_launches": launches, "e2e": e2e,
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                          "traffic": traffic, "peak_source": how,

@@ -67,6 +67,13 @@ class Halo(ctypes.Structure):
                 ("recv_hi", ctypes.c_void_p), ("bytes", ctypes.c_size_t)]
 
 
+class PeerInfo(ctypes.Structure):
+    """fdlbm_peer_info of include/fdlbm.h (plain bytes: can be pickled and sent to another rank)"""
+    _fields_ = [("pid", ctypes.c_int64), ("device", ctypes.c_int32), ("Wl", ctypes.c_int32), ("Hp", ctypes.c_int32),
+                ("dtype", ctypes.c_int32), ("lat", ctypes.c_void_p * 2), ("flags", ctypes.c_void_p),
+                ("ipc_lat", (ctypes.c_ubyte * 64) * 2), ("ipc_flags", ctypes.c_ubyte * 64)]
+
+
 # every symbol include/fdlbm.h declares (tests check the export list against the header)
 _SIGS = {
     "fdlbm_abi_version": (ctypes.c_int, []),
@@ -83,6 +90,8 @@ _SIGS = {
     "fdlbm_stream": (ctypes.c_void_p, [ctypes.c_void_p]),
     "fdlbm_launch_count": (ctypes.c_int64, [ctypes.c_void_p]),
     "fdlbm_halo_regions": (ctypes.c_int, [ctypes.c_void_p, ctypes.POINTER(Halo)]),
+    "fdlbm_peer_export": (ctypes.c_int, [ctypes.c_void_p, ctypes.POINTER(PeerInfo)]),
+    "fdlbm_peer_attach": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int, ctypes.POINTER(PeerInfo)]),
     "fdlbm_pinned_alloc": (ctypes.c_void_p, [ctypes.c_size_t]),
     "fdlbm_pinned_free": (None, [ctypes.c_void_p]),
     "fdlbm_op_stream": (ctypes.c_int, [ctypes.c_int, ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p]),

@@ -5,6 +5,7 @@
 #include <cstdarg>
 #include <cstdio>
 #include <cstring>
+#include <unistd.h>
 #include <string>
 #include <vector>
 
@@ -57,6 +58,13 @@ struct fdlbm_engine {
     cudaEvent_t stage_full[2] = {nullptr, nullptr};           // staging buffer b holds a produced plane
     cudaEvent_t stage_free[2] = {nullptr, nullptr};           // ... and has been consumed
     uint64_t stage_seq = 0;
+    // fused halo exchange over peer memory (fdlbm_peer_attach)
+    uint32_t *flags = nullptr;                                // [0]: low neighbour's progress, [1]: high neighbour's
+    void *peer_lat[2][2] = {{nullptr, nullptr}, {nullptr, nullptr}};  // [side][lattice]
+    uint32_t *peer_flags[2] = {nullptr, nullptr};             // the neighbours' flag words
+    int peer_Wl[2] = {0, 0};
+    bool peer_ipc[2] = {false, false};
+    uint32_t peer_step = 0;                                   // steps taken in peer mode (never reset)
     int cur = 0, pcur = 0;
     int state = ST_EMPTY;
     bool have_geometry = false;
@@ -66,6 +74,7 @@ struct fdlbm_engine {
 
     size_t lat_elems() const { return (size_t)ncols * NPOP * Hp; }
     size_t plane_elems() const { return (size_t)ncols * Hp; }
+    bool peer_mode() const { return peer_flags[0] != nullptr || peer_flags[1] != nullptr; }
     bool has_lo() const { return cfg.x0 > 0 || cfg.x_periodic; }
     bool has_hi() const { return cfg.x1 < cfg.W || cfg.x_periodic; }
 };
@@ -103,7 +112,60 @@ LbmParams<T> make_params(const fdlbm_engine *e, int src, int psrc)
     P.psi_left = (T)c.psi_left;
     P.psi_right = (T)c.psi_right;
     P.f3coef = (T)c.outlet_f3_coef;
+    P.peer_lo = P.peer_hi = nullptr;
+    P.peer_lo_Wl = 0;
     return P;
+}
+
+// ---- stream-ordered flags between neighbouring engines (driver entry points fetched at run time so that the
+// library keeps loading on machines without libcuda) ---------------------------------------------------------
+typedef int (*stream_value32_fn)(cudaStream_t, unsigned long long, unsigned int, unsigned int);
+stream_value32_fn g_write_value = nullptr, g_wait_value = nullptr;
+
+int load_stream_memops()
+{
+    if (g_write_value && g_wait_value) return 0;
+    void *w = nullptr, *q = nullptr;
+    cudaDriverEntryPointQueryResult r1, r2;
+    CU(cudaGetDriverEntryPoint("cuStreamWriteValue32", &w, cudaEnableDefault, &r1));
+    CU(cudaGetDriverEntryPoint("cuStreamWaitValue32", &q, cudaEnableDefault, &r2));
+    if (!w || !q || r1 != cudaDriverEntryPointSuccess || r2 != cudaDriverEntryPointSuccess)
+        return fail(FDLBM_E_CUDA, "stream memory operations are not available from this driver");
+    g_write_value = (stream_value32_fn)w;
+    g_wait_value = (stream_value32_fn)q;
+    return 0;
+}
+
+// wait until both attached neighbours have completed `step` steps (their edge columns of that step are in our
+// ghost columns, and they no longer read the lattice our next step writes their ghosts of)
+int peer_wait(fdlbm_engine *e, uint32_t step)
+{
+    for (int side = 0; side < 2; ++side)
+        if (e->peer_flags[side]) {
+            int rc = g_wait_value(e->stream, (unsigned long long)(uintptr_t)(e->flags + side), step, 0 /* GEQ */);
+            if (rc) return fail(FDLBM_E_CUDA, "cuStreamWaitValue32 failed (%d)", rc);
+        }
+    return 0;
+}
+
+// tell the neighbours that this engine has completed `step` steps: we are the HIGH neighbour of our low
+// neighbour (its flags[1]) and the LOW neighbour of our high neighbour (its flags[0])
+int peer_signal(fdlbm_engine *e, uint32_t step)
+{
+    for (int side = 0; side < 2; ++side)
+        if (e->peer_flags[side]) {
+            int rc = g_write_value(e->stream, (unsigned long long)(uintptr_t)(e->peer_flags[side] + (1 - side)), step, 0);
+            if (rc) return fail(FDLBM_E_CUDA, "cuStreamWriteValue32 failed (%d)", rc);
+        }
+    return 0;
+}
+
+template <typename T>
+void set_peers(const fdlbm_engine *e, LbmParams<T> &P, int dst_lattice)
+{
+    P.peer_lo = (T *)e->peer_lat[0][dst_lattice];
+    P.peer_hi = (T *)e->peer_lat[1][dst_lattice];
+    P.peer_lo_Wl = e->peer_Wl[0];
 }
 
 template <typename T>
@@ -167,6 +229,7 @@ int launch_step(fdlbm_engine *e, bool finalize)
         if (rc) return rc;
     }
     const int lo = e->has_lo() ? -1 : 0, hi = e->Wl + (e->has_hi() ? 1 : 0);
+    if (!finalize && e->peer_mode()) set_peers(e, P, 1 - e->cur);
     if (finalize || e->kernel == FDLBM_KERNEL_TWOPASS) {
         k_psi<T><<<cell_grid(e, hi - lo), TPB, 0, e->stream>>>(P, lo);
         if (finalize)
@@ -187,19 +250,28 @@ template <typename T>
 int do_steps(fdlbm_engine *e, int n)
 {
     if (n <= 0) return 0;
+    const bool peer = e->peer_mode();
+    int rc;
     if (e->state == ST_PRE) {
         // first collision from the caller's macroscopic arrays, in place on lat[cur]
         LbmParams<T> P = make_params<T>(e, 1 - e->cur, e->pcur);  // dst = lat[cur]
+        if (peer) {
+            // the neighbours must be done with whatever still reads their lat[cur] ghosts
+            if ((rc = peer_wait(e, e->peer_step))) return rc;
+            set_peers(e, P, e->cur);
+        }
         k_collide_first<T><<<cell_grid(e, e->Wl), TPB, 0, e->stream>>>(P, field_ptrs<T>(e), (const T *)e->psi[e->pcur]);
         CU(cudaGetLastError());
+        if (peer && (rc = peer_signal(e, ++e->peer_step))) return rc;
         e->launches += 1;
         e->state = ST_POST;
         e->iters += 1;
         n -= 1;
     }
     for (int k = 0; k < n; ++k) {
-        int rc = launch_step<T>(e, false);
-        if (rc) return rc;
+        if (peer && (rc = peer_wait(e, e->peer_step))) return rc;
+        if ((rc = launch_step<T>(e, false))) return rc;
+        if (peer && (rc = peer_signal(e, ++e->peer_step))) return rc;
         e->cur ^= 1;
         e->pcur ^= 1;
         e->iters += 1;
@@ -334,6 +406,7 @@ int get_state_t(fdlbm_engine *e, int col0, int ncw, const fdlbm_fields *out)
         lat = (const T *)e->lat[e->cur];
         psi = (const T *)e->psi[e->pcur];
     } else {
+        if (e->peer_mode() && (rc = peer_wait(e, e->peer_step))) return rc;
         if ((rc = launch_step<T>(e, true))) return rc;  // writes lat[1-cur], psi[1-pcur], fields; no swap
         lat = (const T *)e->lat[1 - e->cur];
         psi = (const T *)e->psi[1 - e->pcur];
@@ -434,6 +507,8 @@ int fdlbm_create(const fdlbm_config *cfg, fdlbm_engine **out)
         CUE(cudaMalloc(&e->psi[k], e->plane_elems() * e->esize));
         CUE(cudaMemsetAsync(e->psi[k], 0, e->plane_elems() * e->esize, e->stream));
     }
+    CUE(cudaMalloc((void **)&e->flags, 256));
+    CUE(cudaMemsetAsync(e->flags, 0, 256, e->stream));
     CUE(cudaMalloc(&e->reflect, e->plane_elems()));
     CUE(cudaMemsetAsync(e->reflect, 0, e->plane_elems(), e->stream));
     CUE(cudaMalloc(&e->solid_bytes, e->plane_elems()));
@@ -464,8 +539,14 @@ void fdlbm_destroy(fdlbm_engine *e)
     cudaSetDevice(e->cfg.device);
     if (e->copy_stream) cudaStreamSynchronize(e->copy_stream);
     if (e->stream) cudaStreamSynchronize(e->stream);
+    for (int side = 0; side < 2; ++side)
+        if (e->peer_ipc[side]) {
+            cudaIpcCloseMemHandle(e->peer_lat[side][0]);
+            cudaIpcCloseMemHandle(e->peer_lat[side][1]);
+            cudaIpcCloseMemHandle(e->peer_flags[side]);
+        }
     void *ptrs[] = {e->lat[0], e->lat[1], e->psi[0], e->psi[1], e->fields, e->reflect, e->solid_bytes,
-                    e->solid, e->inlet, e->outlet, e->staging};
+                    e->solid, e->inlet, e->outlet, e->staging, e->flags};
     for (void *p : ptrs)
         if (p) cudaFree(p);
     if (e->stream) cudaStreamDestroy(e->stream);
@@ -523,8 +604,9 @@ int fdlbm_step(fdlbm_engine *e, int n)
     if (!e) return fail(FDLBM_E_ARG, "null engine");
     if (n < 0) return fail(FDLBM_E_ARG, "negative step count");
     if (e->state == ST_EMPTY) return fail(FDLBM_E_STATE, "set_state must be called before step");
-    if (e->cfg.external_halo && n > 1)
-        return fail(FDLBM_E_ARG, "external_halo engines advance one step per call (halo exchange in between)");
+    if (e->cfg.external_halo && n > 1 && !e->peer_mode())
+        return fail(FDLBM_E_ARG, "external_halo engines advance one step per call (halo exchange in between) "
+                                 "unless their neighbours are attached with fdlbm_peer_attach");
     CU(cudaSetDevice(e->cfg.device));
     return e->cfg.dtype == FDLBM_F64 ? do_steps<double>(e, n) : do_steps<float>(e, n);
 }
@@ -561,6 +643,62 @@ int fdlbm_halo_regions(fdlbm_engine *e, fdlbm_halo *out)
     out->send_hi = b + (size_t)e->Wl * col;
     out->recv_hi = b + (size_t)(e->Wl + G) * col;
     out->bytes = (size_t)G * col;
+    return 0;
+}
+
+int fdlbm_peer_export(fdlbm_engine *e, fdlbm_peer_info *out)
+{
+    if (!e || !out) return fail(FDLBM_E_ARG, "null argument");
+    CU(cudaSetDevice(e->cfg.device));
+    memset(out, 0, sizeof *out);
+    out->pid = (int64_t)getpid();
+    out->device = e->cfg.device;
+    out->Wl = e->Wl;
+    out->Hp = e->Hp;
+    out->dtype = e->cfg.dtype;
+    out->lat[0] = e->lat[0];
+    out->lat[1] = e->lat[1];
+    out->flags = e->flags;
+    static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle size");
+    CU(cudaIpcGetMemHandle((cudaIpcMemHandle_t *)out->ipc_lat[0], e->lat[0]));
+    CU(cudaIpcGetMemHandle((cudaIpcMemHandle_t *)out->ipc_lat[1], e->lat[1]));
+    CU(cudaIpcGetMemHandle((cudaIpcMemHandle_t *)out->ipc_flags, e->flags));
+    return 0;
+}
+
+int fdlbm_peer_attach(fdlbm_engine *e, int side, const fdlbm_peer_info *nb)
+{
+    if (!e || !nb || (side != 0 && side != 1)) return fail(FDLBM_E_ARG, "bad argument");
+    if (!e->cfg.external_halo) return fail(FDLBM_E_ARG, "peer halos need an engine created with external_halo=1");
+    if (nb->Hp != e->Hp || nb->dtype != e->cfg.dtype) return fail(FDLBM_E_ARG, "neighbour has a different H or dtype");
+    if (e->peer_flags[side]) return fail(FDLBM_E_STATE, "side %d is already attached", side);
+    CU(cudaSetDevice(e->cfg.device));
+    int rc = load_stream_memops();
+    if (rc) return rc;
+    if (nb->pid == (int64_t)getpid()) {  // same process: the pointers are directly usable
+        if (nb->device != e->cfg.device) {
+            int can = 0;
+            CU(cudaDeviceCanAccessPeer(&can, e->cfg.device, nb->device));
+            if (!can) return fail(FDLBM_E_CUDA, "device %d cannot access device %d", e->cfg.device, nb->device);
+            cudaError_t pe = cudaDeviceEnablePeerAccess(nb->device, 0);
+            if (pe != cudaSuccess && pe != cudaErrorPeerAccessAlreadyEnabled)
+                return fail(FDLBM_E_CUDA, "cudaDeviceEnablePeerAccess: %s", cudaGetErrorString(pe));
+            cudaGetLastError();
+        }
+        e->peer_lat[side][0] = nb->lat[0];
+        e->peer_lat[side][1] = nb->lat[1];
+        e->peer_flags[side] = (uint32_t *)nb->flags;
+    } else {
+        void *p0 = nullptr, *p1 = nullptr, *pf = nullptr;
+        CU(cudaIpcOpenMemHandle(&p0, *(const cudaIpcMemHandle_t *)nb->ipc_lat[0], cudaIpcMemLazyEnablePeerAccess));
+        CU(cudaIpcOpenMemHandle(&p1, *(const cudaIpcMemHandle_t *)nb->ipc_lat[1], cudaIpcMemLazyEnablePeerAccess));
+        CU(cudaIpcOpenMemHandle(&pf, *(const cudaIpcMemHandle_t *)nb->ipc_flags, cudaIpcMemLazyEnablePeerAccess));
+        e->peer_lat[side][0] = p0;
+        e->peer_lat[side][1] = p1;
+        e->peer_flags[side] = (uint32_t *)pf;
+        e->peer_ipc[side] = true;
+    }
+    e->peer_Wl[side] = nb->Wl;
     return 0;
 }
 

@@ -33,6 +33,10 @@ struct LbmParams {
     int H, Hp, Wl, gx0, W;    // gx0 = global column of local column 0
     int y_wall, x_periodic, zou_he;
     T inv_tau, gamma, a, kappa, eta6m, M, psi_wall, psi_left, psi_right, f3coef;
+    // slab neighbours' dst lattices, mapped over NVLink (peer memory), or nullptr: the step kernel stores its
+    // two edge columns straight into their ghost columns (halo exchange fused into the step)
+    T *peer_lo, *peer_hi;
+    int peer_lo_Wl;           // owned columns of the low-side neighbour (its high ghosts are columns Wl, Wl+1)
 };
 
 // macroscopic outputs of the finalize pass / inputs of the first collision, each [(xl+G)*Hp + y]
@@ -349,14 +353,23 @@ __device__ __forceinline__ void collide(const LbmParams<T> &P, const Macro<T> &m
 }
 
 template <typename T>
-__device__ __forceinline__ void store_cell(const LbmParams<T> &P, int xl, int y, const T f[9], const T g[9])
+__device__ __forceinline__ void store_cell_at(T *lat, int Hp, int xl, int y, const T f[9], const T g[9])
 {
-    T *o = P.dst + lat_idx(P.Hp, xl, 0, y);
+    T *o = lat + lat_idx(Hp, xl, 0, y);
 #pragma unroll
     for (int i = 0; i < 9; ++i) {
-        o[(size_t)i * P.Hp] = f[i];
-        o[(size_t)(9 + i) * P.Hp] = g[i];
+        o[(size_t)i * Hp] = f[i];
+        o[(size_t)(9 + i) * Hp] = g[i];
     }
+}
+
+template <typename T>
+__device__ __forceinline__ void store_cell(const LbmParams<T> &P, int xl, int y, const T f[9], const T g[9])
+{
+    store_cell_at(P.dst, P.Hp, xl, y, f, g);
+    // halo push: the two edge columns also land in the neighbours' ghost columns (peer stores over NVLink)
+    if (P.peer_lo && xl < G) store_cell_at(P.peer_lo, P.Hp, P.peer_lo_Wl + xl, y, f, g);
+    if (P.peer_hi && xl >= P.Wl - G) store_cell_at(P.peer_hi, P.Hp, xl - P.Wl, y, f, g);
 }
 
 }  // namespace fdlbm

@@ -131,6 +131,18 @@ class Engine:
         """raw cudaStream_t of the engine (int)"""
         return int(nat.lib().fdlbm_stream(self._h) or 0)
 
+    def peer_export(self):
+        """bytes describing this engine's lattices and flag words (fdlbm_peer_info) for a neighbouring engine"""
+        info = nat.PeerInfo()
+        nat.check(nat.lib().fdlbm_peer_export(self._h, ctypes.byref(info)))
+        return bytes(info)
+
+    def peer_attach(self, side, info_bytes):
+        """side 0: the neighbour owns the columns just below x0; side 1: just above x1.  Afterwards the step
+        kernel pushes its edge columns into that neighbour's ghost columns and step(n) may take many steps."""
+        info = nat.PeerInfo.from_buffer_copy(info_bytes)
+        nat.check(nat.lib().fdlbm_peer_attach(self._h, int(side), ctypes.byref(info)))
+
     def halo_regions(self):
         h = nat.Halo()
         nat.check(nat.lib().fdlbm_halo_regions(self._h, ctypes.byref(h)))

@@ -8,8 +8,13 @@ Two columns, not one: the collision at an edge cell needs the NEW psi on its one
 pulled one column further out.  With Zou-He faces no wrap-around message is needed (the wrapped
 populations are overwritten on the faces); x-periodic grids (validation.py) close the ring.
 
-torch.distributed is plumbing only: NCCL send/recv on raw device pointers of the engine, enqueued on the
-engine's own CUDA stream (no host synchronisation between steps).
+Two transports:
+  * halo="peer" (default on GPUs): the exchange is FUSED into the step kernel -- it stores its edge columns
+    straight into the neighbours' ghost columns through peer-mapped memory (CUDA IPC over NVLink), and the steps
+    of neighbouring engines are ordered by stream-side flags; torch.distributed only carries the IPC handles
+    once.  No collective library on the data path, no host involvement between steps.
+  * halo="nccl": ncclSend/ncclRecv (torch.distributed batch_isend_irecv) on raw device pointers of the engine,
+    enqueued on the engine's own CUDA stream; also what the CPU (gloo) protocol tests drive.
 """
 import numpy as np
 
@@ -33,12 +38,35 @@ class SlabRunner:
     """Drives one engine of a slab-decomposed run.  `engine` needs step(n), get_state(...) and either
     halo_regions() (the CUDA Engine) or halo_tensors() (any object handing out torch tensors)."""
 
-    def __init__(self, engine, rank=0, world=1, periodic=False):
+    def __init__(self, engine, rank=0, world=1, periodic=False, halo="nccl"):
         self.e, self.rank, self.world, self.periodic = engine, int(rank), int(world), bool(periodic)
         self.left = rank - 1 if rank > 0 else (world - 1 if periodic else None)
         self.right = rank + 1 if rank < world - 1 else (0 if periodic else None)
         self._cache = {}
         self._stream = None
+        self.halo = halo if self.world > 1 else "none"
+        if self.halo == "peer":
+            self._attach_peers()
+
+    def _attach_peers(self):
+        """all-gather the engines' peer descriptions (IPC handles) and attach the neighbours"""
+        import torch.distributed as dist
+        infos = [None] * self.world
+        dist.all_gather_object(infos, self.e.peer_export())
+        if self.left is not None:
+            self.e.peer_attach(0, infos[self.left])
+        if self.right is not None:
+            self.e.peer_attach(1, infos[self.right])
+        dist.barrier()
+
+    def set_state(self, **kw):
+        """engine.set_state on every rank, then a barrier: a neighbour's first step writes into this rank's
+        ghost columns, which must not happen before this rank has finished loading its state"""
+        self.e.set_state(**kw)
+        if self.world > 1:
+            import torch.distributed as dist
+            self.e.sync()
+            dist.barrier()
 
     # -- halo buffers ------------------------------------------------------------------------------
     def _tensors(self):
@@ -85,7 +113,7 @@ class SlabRunner:
 
     # -- run ---------------------------------------------------------------------------------------
     def step(self, n=1):
-        if self.world == 1:
+        if self.world == 1 or self.halo == "peer":
             self.e.step(n)
             return
         for _ in range(int(n)):
@@ -93,5 +121,6 @@ class SlabRunner:
             self.e.step(1)
 
     def get_state(self, names=("psi", "rho", "ux", "uy"), **kw):
-        self.exchange()
+        if self.halo != "peer":
+            self.exchange()
         return self.e.get_state(names, **kw)

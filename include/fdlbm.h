@@ -123,6 +123,24 @@ typedef struct {
 } fdlbm_halo;
 int fdlbm_halo_regions(fdlbm_engine *e, fdlbm_halo *out);
 
+/* Halo exchange FUSED into the step (preferred on NVLink): once the neighbours are attached, the step
+ * kernel stores its two edge columns straight into the neighbours' ghost columns through peer-mapped
+ * memory, and the steps of neighbouring engines are ordered by stream-side flags (cuStreamWriteValue32 /
+ * cuStreamWaitValue32 on peer memory) -- no host synchronisation, no collective library on the data path,
+ * and fdlbm_step(e, n) may advance many steps per call.  Every engine of a run must take the same
+ * sequence of set_state / step calls.
+ *   fdlbm_peer_export: describe this engine (CUDA IPC handles of its two lattices and its flag words,
+ *                      plus raw pointers for engines living in the same process);
+ *   fdlbm_peer_attach: side 0 = `nb` owns the columns just below x0, side 1 = just above x1. */
+typedef struct {
+    int64_t pid;                /* process that owns the memory */
+    int32_t device, Wl, Hp, dtype;
+    void *lat[2], *flags;       /* valid inside process `pid` */
+    unsigned char ipc_lat[2][64], ipc_flags[64]; /* cudaIpcMemHandle_t */
+} fdlbm_peer_info;
+int fdlbm_peer_export(fdlbm_engine *e, fdlbm_peer_info *out);
+int fdlbm_peer_attach(fdlbm_engine *e, int side, const fdlbm_peer_info *nb);
+
 /* page-locked host memory for the e2e path */
 void *fdlbm_pinned_alloc(size_t bytes);
 void fdlbm_pinned_free(void *p);

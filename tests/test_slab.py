@@ -145,3 +145,46 @@ def test_slabs_on_one_gpu_are_bit_identical_to_the_single_slab_run(golden, name,
         for k in got:
             assert np.array_equal(got[k], want[k][..., x0:x1]), (name, r, k)
         e.close()
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("name,nslab,kernel", [("fp_small", 2, "fused"), ("fp_small", 3, "fused"), ("fg_small", 2, "twopass"),
+                                                ("va_small", 2, "fused"), ("va_small", 3, "fused")])
+def test_peer_halo_engines_are_bit_identical_to_the_single_slab_run(golden, name, nslab, kernel):
+    """halo exchange fused into the step kernel (stores into the neighbours' ghost columns + stream flags):
+    N engines in one process on one device, many steps per call, same bits as one engine."""
+    from tests import helpers as hp
+    from fingering_dynamics_b200.slab import slab_bounds
+    d = golden(name)
+    W = int(d["W"])
+    periodic = name.startswith("va")
+    s0 = hp.state_for_engine(d, "s0")
+    ref = hp.ENGINES[name](d)
+    ref.set_state(**s0)
+    ref.step(12)
+    want = ref.get_state(("f", "g", "psi", "rho", "ux", "uy"))
+    ref.close()
+
+    engs = [hp.ENGINES[name](d, slab=slab_bounds(W, nslab, r), external_halo=True, kernel=kernel) for r in range(nslab)]
+    infos = [e.peer_export() for e in engs]
+    for r, e in enumerate(engs):
+        left = r - 1 if r > 0 else (nslab - 1 if periodic else None)
+        right = r + 1 if r < nslab - 1 else (0 if periodic else None)
+        if left is not None:
+            e.peer_attach(0, infos[left])
+        if right is not None:
+            e.peer_attach(1, infos[right])
+    for e in engs:
+        e.set_state(**s0)
+    for e in engs:
+        e.sync()
+    for n in (1, 4, 7):            # many steps per call, no host involvement in between
+        for e in engs:
+            e.step(n)
+    for r, e in enumerate(engs):
+        x0, x1 = slab_bounds(W, nslab, r)
+        got = e.get_state(("f", "g", "psi", "rho", "ux", "uy"))
+        for k in got:
+            assert np.array_equal(got[k], want[k][..., x0:x1]), (name, r, k)
+    for e in engs:
+        e.close()
