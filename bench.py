@@ -183,7 +183,27 @@ def main():
                  psi_wall=c["psi_wall"], zou_he="fp", inlet_ux=c["inlet_ux"], outlet_ux=c["outlet_ux"], dtype=args.dtype,
                  kernel=args.kernel, device=local, slab=(x0, x1), external_halo=world > 1)
     eng.set_geometry(solid, refl, col0=max(0, x0 - 2))
-    runner = SlabRunner(eng, rank, world, halo=args.halo)
+    halo = args.halo
+    if world > 1 and halo == "peer":
+        # peer-mapped halos need CUDA IPC between the ranks; if any rank cannot attach, all use NCCL send/recv
+        try:
+            runner = SlabRunner(eng, rank, world, halo="peer")
+            ok = 1
+        except Exception as ex:  # noqa: BLE001
+            print("rank %d: peer halo unavailable (%s), using NCCL" % (rank, ex), file=sys.stderr)
+            ok = 0
+        t_ok = torch.tensor([ok], device="cuda")
+        dist.all_reduce(t_ok, op=dist.ReduceOp.MIN)
+        if int(t_ok.item()) == 0:
+            halo = "nccl"
+            eng.close()
+            eng = Engine(H, W, tau=c["tau"], gamma=c["gamma"], a=c["a"], kappa=c["kappa"], Eta_n=c["Eta_n"], M=c["M"],
+                         psi_wall=c["psi_wall"], zou_he="fp", inlet_ux=c["inlet_ux"], outlet_ux=c["outlet_ux"],
+                         dtype=args.dtype, kernel=args.kernel, device=local, slab=(x0, x1), external_halo=True)
+            eng.set_geometry(solid, refl, col0=max(0, x0 - 2))
+            runner = SlabRunner(eng, rank, world, halo="nccl")
+    else:
+        runner = SlabRunner(eng, rank, world, halo=halo)
     stream = torch.cuda.ExternalStream(eng.stream, device=torch.device("cuda", local))
 
     def barrier():
@@ -259,7 +279,7 @@ def main():
                        "kernel": args.kernel, "l2": "state (%.1f GB per lattice copy) far exceeds the 126 MB L2; no flush needed"
                                                     % (cells_local * 18 * (8 if args.dtype == "f64" else 4) / 1e9),
                        "parallelism": "slab%d" % world,
-                       "halo": ("in-kernel peer stores over NVLink + stream flags" if args.halo == "peer" else "NCCL send/recv")
+                       "halo": ("in-kernel peer stores over NVLink + stream flags" if halo == "peer" else "NCCL send/recv")
                        if world > 1 else "none"},
             "clocks": clocks.summary(), "gpu_launches": launches, "e2e": e2e,
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
