@@ -90,6 +90,10 @@ _SIGS = {
     "fdlbm_stream": (ctypes.c_void_p, [ctypes.c_void_p]),
     "fdlbm_launch_count": (ctypes.c_int64, [ctypes.c_void_p]),
     "fdlbm_halo_regions": (ctypes.c_int, [ctypes.c_void_p, ctypes.POINTER(Halo)]),
+    "fdlbm_checkpoint_bytes": (ctypes.c_size_t, [ctypes.c_void_p]),
+    "fdlbm_checkpoint_save": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_size_t]),
+    "fdlbm_checkpoint_load": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_size_t]),
+    "fdlbm_count_nonfinite": (ctypes.c_int, [ctypes.c_void_p, ctypes.POINTER(ctypes.c_int64)]),
     "fdlbm_peer_export": (ctypes.c_int, [ctypes.c_void_p, ctypes.POINTER(PeerInfo)]),
     "fdlbm_peer_attach": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int, ctypes.POINTER(PeerInfo)]),
     "fdlbm_pinned_alloc": (ctypes.c_void_p, [ctypes.c_size_t]),

@@ -646,6 +646,92 @@ int fdlbm_halo_regions(fdlbm_engine *e, fdlbm_halo *out)
     return 0;
 }
 
+// checkpoint blob: header | lat[cur] | psi[pcur] | fields (9 planes)
+struct CkptHeader {
+    char magic[8];
+    int32_t H, W, x0, x1, dtype, state, Hp, ncols;
+    int64_t iters;
+};
+
+size_t fdlbm_checkpoint_bytes(const fdlbm_engine *e)
+{
+    if (!e) return 0;
+    return sizeof(CkptHeader) + (e->lat_elems() + 10 * e->plane_elems()) * e->esize;
+}
+
+int fdlbm_checkpoint_save(fdlbm_engine *e, void *host, size_t bytes)
+{
+    if (!e || !host) return fail(FDLBM_E_ARG, "null argument");
+    if (e->state == ST_EMPTY) return fail(FDLBM_E_STATE, "no state loaded");
+    if (bytes < fdlbm_checkpoint_bytes(e)) return fail(FDLBM_E_ARG, "checkpoint buffer too small");
+    CU(cudaSetDevice(e->cfg.device));
+    int rc = ensure_fields(e);
+    if (rc) return rc;
+    CkptHeader h{};
+    memcpy(h.magic, "FDLBMCK1", 8);
+    h.H = e->cfg.H, h.W = e->cfg.W, h.x0 = e->cfg.x0, h.x1 = e->cfg.x1, h.dtype = e->cfg.dtype;
+    h.state = e->state, h.Hp = e->Hp, h.ncols = e->ncols, h.iters = e->iters;
+    char *p = (char *)host;
+    memcpy(p, &h, sizeof h);
+    p += sizeof h;
+    CU(cudaStreamSynchronize(e->stream));
+    CU(cudaMemcpy(p, e->lat[e->cur], e->lat_elems() * e->esize, cudaMemcpyDeviceToHost));
+    p += e->lat_elems() * e->esize;
+    CU(cudaMemcpy(p, e->psi[e->pcur], e->plane_elems() * e->esize, cudaMemcpyDeviceToHost));
+    p += e->plane_elems() * e->esize;
+    CU(cudaMemcpy(p, e->fields, 9 * e->plane_elems() * e->esize, cudaMemcpyDeviceToHost));
+    return 0;
+}
+
+int fdlbm_checkpoint_load(fdlbm_engine *e, const void *host, size_t bytes)
+{
+    if (!e || !host) return fail(FDLBM_E_ARG, "null argument");
+    if (bytes < fdlbm_checkpoint_bytes(e)) return fail(FDLBM_E_ARG, "checkpoint blob too small for this engine");
+    if (!e->have_geometry) return fail(FDLBM_E_STATE, "set_geometry must be called before loading a checkpoint");
+    CkptHeader h;
+    memcpy(&h, host, sizeof h);
+    if (memcmp(h.magic, "FDLBMCK1", 8) != 0) return fail(FDLBM_E_ARG, "not a checkpoint blob");
+    if (h.H != e->cfg.H || h.W != e->cfg.W || h.x0 != e->cfg.x0 || h.x1 != e->cfg.x1 || h.dtype != e->cfg.dtype ||
+        h.Hp != e->Hp || h.ncols != e->ncols)
+        return fail(FDLBM_E_ARG, "checkpoint was taken from a different grid / slab / dtype");
+    CU(cudaSetDevice(e->cfg.device));
+    int rc = ensure_fields(e);
+    if (rc) return rc;
+    CU(cudaStreamSynchronize(e->stream));
+    const char *p = (const char *)host + sizeof h;
+    e->cur = 0;
+    e->pcur = 0;
+    CU(cudaMemcpy(e->lat[0], p, e->lat_elems() * e->esize, cudaMemcpyHostToDevice));
+    p += e->lat_elems() * e->esize;
+    CU(cudaMemset(e->lat[1], 0, e->lat_elems() * e->esize));
+    CU(cudaMemcpy(e->psi[0], p, e->plane_elems() * e->esize, cudaMemcpyHostToDevice));
+    p += e->plane_elems() * e->esize;
+    CU(cudaMemcpy(e->fields, p, 9 * e->plane_elems() * e->esize, cudaMemcpyHostToDevice));
+    e->state = h.state;
+    e->iters = h.iters;
+    return 0;
+}
+
+int fdlbm_count_nonfinite(fdlbm_engine *e, int64_t *n_bad)
+{
+    if (!e || !n_bad) return fail(FDLBM_E_ARG, "null argument");
+    if (e->state == ST_EMPTY) return fail(FDLBM_E_STATE, "no state loaded");
+    CU(cudaSetDevice(e->cfg.device));
+    unsigned long long *d = (unsigned long long *)(e->flags + 16);  // spare words of the flag block
+    CU(cudaMemsetAsync(d, 0, sizeof *d, e->stream));
+    if (e->cfg.dtype == FDLBM_F64)
+        k_count_nonfinite<double><<<cell_grid(e, e->Wl), TPB, 0, e->stream>>>((const double *)e->lat[e->cur], e->cfg.H, e->Hp, d);
+    else
+        k_count_nonfinite<float><<<cell_grid(e, e->Wl), TPB, 0, e->stream>>>((const float *)e->lat[e->cur], e->cfg.H, e->Hp, d);
+    CU(cudaGetLastError());
+    e->launches += 1;
+    unsigned long long h = 0;
+    CU(cudaMemcpyAsync(&h, d, sizeof h, cudaMemcpyDeviceToHost, e->stream));
+    CU(cudaStreamSynchronize(e->stream));
+    *n_bad = (int64_t)h;
+    return 0;
+}
+
 int fdlbm_peer_export(fdlbm_engine *e, fdlbm_peer_info *out)
 {
     if (!e || !out) return fail(FDLBM_E_ARG, "null argument");

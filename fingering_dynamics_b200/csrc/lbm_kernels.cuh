@@ -151,6 +151,21 @@ __global__ void k_transpose_out(const TS *__restrict__ base, size_t xstride, int
     }
 }
 
+// count non-finite populations of the owned columns (watchdog standing in for np.seterr(all='raise'))
+template <typename T>
+__global__ void __launch_bounds__(TPB) k_count_nonfinite(const T *__restrict__ lat, int H, int Hp, unsigned long long *n_bad)
+{
+    const int y = blockIdx.x * TPB + threadIdx.x, xl = blockIdx.y;
+    unsigned bad = 0;
+    if (y < H) {
+        const T *s = lat + lat_idx(Hp, xl, 0, y);
+#pragma unroll
+        for (int i = 0; i < NPOP; ++i) bad += !isfinite(s[(size_t)i * Hp]);
+    }
+    bad = __reduce_add_sync(0xffffffffu, bad);
+    if ((threadIdx.x & 31) == 0 && bad) atomicAdd(n_bad, (unsigned long long)bad);
+}
+
 // solid bytes [(xl+G)*Hp + y] -> bitfield words [(xl+G)*(Hp/32) + y/32]; one warp ballot per word
 __global__ void k_pack_solid(const uint8_t *__restrict__ bytes, uint32_t *__restrict__ bits, size_t n_cells)
 {

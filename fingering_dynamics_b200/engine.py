@@ -131,6 +131,37 @@ class Engine:
         """raw cudaStream_t of the engine (int)"""
         return int(nat.lib().fdlbm_stream(self._h) or 0)
 
+    # -- restart / watchdog ---------------------------------------------------------------------------
+    def checkpoint(self):
+        """opaque bytes of the raw device state; a run continued from restore() is bit-identical"""
+        n = int(nat.lib().fdlbm_checkpoint_bytes(self._h))
+        buf = np.empty(n, dtype=np.uint8)
+        nat.check(nat.lib().fdlbm_checkpoint_save(self._h, nat.ptr(buf), n))
+        return buf
+
+    def restore(self, blob):
+        """load a checkpoint() blob taken from an engine of the same grid / slab / dtype (geometry must be set)"""
+        buf = np.ascontiguousarray(np.frombuffer(blob, dtype=np.uint8))
+        nat.check(nat.lib().fdlbm_checkpoint_load(self._h, nat.ptr(buf), buf.size))
+
+    def save(self, path):
+        np.save(path, self.checkpoint(), allow_pickle=False)
+
+    def load(self, path):
+        self.restore(np.load(path, allow_pickle=False))
+
+    def count_nonfinite(self):
+        n = ctypes.c_int64(0)
+        nat.check(nat.lib().fdlbm_count_nonfinite(self._h, ctypes.byref(n)))
+        return int(n.value)
+
+    def check_finite(self):
+        """the reference runs under np.seterr(all='raise') (fingering_periodic.py:497): a blow-up is a
+        FloatingPointError there; same here, on demand"""
+        n = self.count_nonfinite()
+        if n:
+            raise FloatingPointError("%d non-finite populations after %d iterations" % (n, self.iterations))
+
     def peer_export(self):
         """bytes describing this engine's lattices and flag words (fdlbm_peer_info) for a neighbouring engine"""
         info = nat.PeerInfo()

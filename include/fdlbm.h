@@ -123,6 +123,17 @@ typedef struct {
 } fdlbm_halo;
 int fdlbm_halo_regions(fdlbm_engine *e, fdlbm_halo *out);
 
+/* Exact restart (absent in the reference, whose runs keep everything in RAM): the raw device state --
+ * current lattice with ghosts, psi, macroscopic scratch, counters -- as an opaque blob.  A run continued
+ * from a loaded checkpoint is bit-identical to the uninterrupted run.  Geometry is not part of the blob. */
+size_t fdlbm_checkpoint_bytes(const fdlbm_engine *e);
+int fdlbm_checkpoint_save(fdlbm_engine *e, void *host, size_t bytes);
+int fdlbm_checkpoint_load(fdlbm_engine *e, const void *host, size_t bytes);
+
+/* Watchdog standing in for np.seterr(all='raise') (fingering_periodic.py:497): counts non-finite
+ * populations of the owned columns of the current state into *n_bad. */
+int fdlbm_count_nonfinite(fdlbm_engine *e, int64_t *n_bad);
+
 /* Halo exchange FUSED into the step (preferred on NVLink): once the neighbours are attached, the step
  * kernel stores its two edge columns straight into the neighbours' ghost columns through peer-mapped
  * memory, and the steps of neighbouring engines are ordered by stream-side flags (cuStreamWriteValue32 /

@@ -196,3 +196,74 @@ def test_ops_match_reference_fixtures(golden):
         assert hp.rel_err(gx, d[pre + "_nabla_psix"]) <= 1e-14
         assert hp.rel_err(gy, d[pre + "_nabla_psiy"]) <= 1e-14
         assert hp.rel_err(lap, d[pre + "_nabla_psi2"]) <= 1e-14
+
+
+def test_checkpoint_restart_is_bit_exact_and_watchdog_fires(golden):
+    from fingering_dynamics_b200 import _native as nat
+    d = golden("fp_small")
+    e = hp.fp_engine(d)
+    e.set_state(**hp.state_for_engine(d, "s0"))
+    e.step(7)
+    blob = e.checkpoint()
+    e.step(9)
+    want = e.get_state(("f", "g", "psi", "rho"))
+    assert e.count_nonfinite() == 0
+    e.check_finite()
+    e.close()
+    e2 = hp.fp_engine(d)
+    e2.restore(blob)
+    assert e2.iterations == 7
+    e2.step(9)
+    got = e2.get_state(("f", "g", "psi", "rho"))
+    for k in want:
+        assert np.array_equal(got[k], want[k]), k
+    # a poisoned state is reported like np.seterr(all='raise') would
+    bad = hp.state_for_engine(d, "s0")
+    bad["f"] = bad["f"].copy()
+    bad["f"][3, 5, 7] = np.nan
+    e2.set_state(**bad)
+    e2.step(3)
+    assert e2.count_nonfinite() > 0
+    with pytest.raises(FloatingPointError):
+        e2.check_finite()
+    e2.close()
+    # a blob from another grid is refused
+    e3 = hp.fg_engine(golden("fg_small"))
+    with pytest.raises(nat.FdlbmError):
+        e3.restore(blob)
+    e3.close()
+
+
+def test_fp32_interface_position(golden):
+    """fp32 vs fp64 on the wettability case: displacement of the interface (psi = 0 crossings)"""
+    from fingering_dynamics_b200 import postprocess as pp
+    d = golden("va_small_wet")
+    out = {}
+    for dt in ("f64", "f32"):
+        e = hp.va_engine(d, dtype=dt)
+        e.set_state(**hp.state_for_engine(d, "s0"))
+        e.step(40)
+        out[dt] = e.get_state(("psi",))["psi"]
+        e.close()
+    assert pp.interface_shift(out["f64"], d["s40_psi"]) <= 1e-9
+    assert pp.interface_shift(out["f32"], d["s40_psi"]) <= 1e-3          # stated fp32 effect: < 0.001 cell
+
+
+def test_wettability_sweep_orders_the_contact_angles(monkeypatch):
+    """validation.py at its shipped size (200x250, droplet r=36 on the bottom wall) for three wall
+    wettabilities: the less the wall repels the droplet phase, the smaller the contact angle."""
+    from fingering_dynamics_b200 import postprocess as pp, geometry as geo
+    from fingering_dynamics_b200.lattice_boltzmann import validation as VA, _compute
+    theta = {}
+    # (with the shipped constants the reference itself -- and the oracle -- blow up within 100 steps for
+    # psi_wall >= 0.1; the picture in the reference's README was made with other parameters)
+    for wall in (-0.3, -0.15, 0.0):
+        monkeypatch.setattr(VA, "psi_wall", wall)
+        cm = VA.Compute()
+        _compute.run_loop(cm, geo.reflect_bits_wall_rows(VA.H, VA.W, 0, VA.H - 1), 1500)
+        assert np.isfinite(cm.psi).all()
+        assert abs(cm.rho.sum() - VA.H * VA.W) <= 1e-9 * VA.H * VA.W      # closed box: mass conserved
+        theta[wall] = pp.droplet_contact_angle(cm.psi)
+    assert theta[0.0] < theta[-0.15] < theta[-0.3], theta
+    # the oracle gives 154.0, 157.2, 161.1 degrees after 1500 steps (the droplet starts tangent to the wall)
+    assert abs(theta[0.0] - 154.0) < 0.5 and abs(theta[-0.3] - 161.1) < 0.5, theta

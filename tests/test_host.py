@@ -144,3 +144,15 @@ def test_fp_constants_match_reference_fixture(golden):
     for k in ("tau", "gamma", "a", "kappa", "Eta_n", "M", "u0", "psi_wall"):
         assert c[k] == float(d["c_" + k]), k
     assert np.array_equal(c["inlet_ux"], d["inlet_ux"])
+
+
+def test_contact_angle_estimator_on_analytic_caps():
+    from fingering_dynamics_b200 import postprocess as pp
+    H, W = 120, 200
+    yy, xx = np.mgrid[:H, :W]
+    for th in (60.0, 90.0, 120.0):
+        R = 50.0
+        yc = -0.5 - R * np.cos(np.radians(th))   # the wall is half a cell below row 0
+        psi = np.tanh((R - np.sqrt((xx - 100.3) ** 2 + (yy - yc) ** 2)) / 1.5)
+        assert abs(pp.droplet_contact_angle(psi) - th) < 0.5
+    assert pp.interface_shift(psi, np.roll(psi, 1, axis=1)) == pytest.approx(1.0, abs=1e-6)
