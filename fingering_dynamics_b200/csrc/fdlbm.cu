@@ -11,6 +11,7 @@
 
 #include "lbm_kernels.cuh"
 #include "lbm_fused.cuh"
+#include "lbm_fused_vec.cuh"
 
 using namespace fdlbm;
 
@@ -238,7 +239,7 @@ int launch_step(fdlbm_engine *e, bool finalize)
             k_step_twopass<T, false><<<cell_grid(e, e->Wl), TPB, 0, e->stream>>>(P, field_ptrs<T>(e));
         e->launches += 2;
     } else {
-        int rc = launch_fused<T>(P, e->stream);
+        int rc = launch_fused_auto<T>(P, e->stream);
         if (rc) return fail(FDLBM_E_CUDA, "fused launch configuration failed (%d)", rc);
         e->launches += 1;
     }
