@@ -96,6 +96,17 @@ __device__ __forceinline__ void pull(const LbmParams<T> &P, int xl, int y, int b
         if (bits & 0x40u) s7 = o + 5 * Hp;
         if (bits & 0x80u) s8 = o + 6 * Hp;
     }
+#ifdef FDLBM_LDCS   // streaming (evict-first) loads: every population is read exactly once per step
+    v[0] = __ldcs(c0 + y);
+    v[1] = __ldcs(s1);
+    v[2] = __ldcs(s2);
+    v[3] = __ldcs(s3);
+    v[4] = __ldcs(s4);
+    v[5] = __ldcs(s5);
+    v[6] = __ldcs(s6);
+    v[7] = __ldcs(s7);
+    v[8] = __ldcs(s8);
+#else
     v[0] = c0[y];
     v[1] = *s1;
     v[2] = *s2;
@@ -105,6 +116,7 @@ __device__ __forceinline__ void pull(const LbmParams<T> &P, int xl, int y, int b
     v[6] = *s6;
     v[7] = *s7;
     v[8] = *s8;
+#endif
 }
 
 // Zou-He rules for g on the faces (fingering_periodic.py:278-324, fingering.py:305-390).
@@ -358,8 +370,13 @@ __device__ __forceinline__ void store_cell_at(T *lat, int Hp, int xl, int y, con
     T *o = lat + lat_idx(Hp, xl, 0, y);
 #pragma unroll
     for (int i = 0; i < 9; ++i) {
+#ifdef FDLBM_STCS   // streaming stores: the written lattice is not read again before the next step
+        __stcs(o + (size_t)i * Hp, f[i]);
+        __stcs(o + (size_t)(9 + i) * Hp, g[i]);
+#else
         o[(size_t)i * Hp] = f[i];
         o[(size_t)(9 + i) * Hp] = g[i];
+#endif
     }
 }
 

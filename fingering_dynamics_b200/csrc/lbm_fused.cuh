@@ -44,7 +44,10 @@ namespace fdlbm {
 constexpr int FUSED_TY = FDLBM_FUSED_TY;  // rows per strip = threads per CTA
 constexpr int FUSED_D = FDLBM_FUSED_D;    // cp.async prefetch distance in columns
 constexpr bool FUSED_STAGE_F = FDLBM_STAGE_F != 0;
-constexpr int FUSED_L2_AHEAD = 3;         // L2 prefetch distance of the f columns (registers path)
+#ifndef FDLBM_L2_AHEAD
+#define FDLBM_L2_AHEAD 2
+#endif
+constexpr int FUSED_L2_AHEAD = FDLBM_L2_AHEAD;  // L2 prefetch distance of the f columns (0 = off)
 
 __device__ __forceinline__ void cp_async16(void *smem, const void *gmem)
 {
@@ -260,7 +263,7 @@ __global__ void __launch_bounds__(TY, sizeof(T) == 8 ? FDLBM_FUSED_MINB64 : FDLB
             constexpr int LPP = (TY * (int)sizeof(T) + 127) / 128;  // lines per population row
             const int cf = x + FUSED_L2_AHEAD;
             const int tt = TY - 1 - t;  // the cp.async issue above kept the low warps busy: use the high ones
-            if (tt < 9 * LPP && cf <= xe + 1) {
+            if (FUSED_L2_AHEAD > 0 && tt < 9 * LPP && cf <= xe + 1) {
                 const int pop = tt / LPP, ln = tt - pop * LPP;
                 const int yy = y0 + ln * (128 / (int)sizeof(T));
                 if (yy < H) prefetch_l2(P.src + lat_idx(Hp, cf, pop, yy));
