@@ -142,11 +142,15 @@ def main():
     ap.add_argument("--dtype", default="f64", choices=["f64", "f32"])
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--kernel", default="auto", choices=["auto", "fused", "twopass"])
-    ap.add_argument("--H", type=int, default=H_DEFAULT)
+    ap.add_argument("--workload", default="c4", choices=["c4", "c5"],
+                    help="c4: BASELINE configs[3], 8192x2048 per GPU (weak scaling); c5: configs[4], 32768x8192 in total, "
+                         "slab-decomposed over the GPUs (strong scaling)")
+    ap.add_argument("--H", type=int, default=0)
     ap.add_argument("--W", type=int, default=0, help="global columns (default 8192 per GPU)")
     ap.add_argument("--halo", default="peer", choices=["peer", "nccl"], help="slab halo transport for N>1")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--pageable", action="store_true", help="host arrays in pageable memory (very large grids)")
     args = ap.parse_args()
     if args.impl == "reference":
         return reference_arm(args)
@@ -164,17 +168,21 @@ def main():
     if world > 1:
         import torch.distributed as dist
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
-    H = args.H
-    W = args.W or W_PER_GPU * world
+    if args.workload == "c5":
+        H, W, scaling = args.H or 8192, args.W or 32768, "strong"
+        args.pageable = True   # 38.7 GB of populations per lattice copy: too much to page-lock
+    else:
+        H, W, scaling = args.H or H_DEFAULT, args.W or W_PER_GPU * world, "weak"
     x0, x1 = slab_bounds(W, world, rank)
     K, Wm = args.steps, max(args.warmup, 3)
 
     c = syn.fp_constants(H)
     solid, refl = syn.porous_geometry(H, W, col0=max(0, x0 - 2), ncols=min(W, x1 + 2) - max(0, x0 - 2))
     own = slice(x0 - max(0, x0 - 2), x0 - max(0, x0 - 2) + (x1 - x0))
-    st = syn.fp_initial_state(np.ascontiguousarray(solid[:, own]), c, col0=x0, alloc=pinned_empty)
+    alloc = np.zeros if args.pageable else pinned_empty
+    st = syn.fp_initial_state(np.ascontiguousarray(solid[:, own]), c, col0=x0, alloc=alloc)
     for k in list(st):  # every array of the e2e job lives in page-locked host memory
-        if k not in ("f", "g"):
+        if k not in ("f", "g") and not args.pageable:
             pin = pinned_empty(st[k].shape)
             pin[...] = st[k]
             st[k] = pin
@@ -271,7 +279,7 @@ def main():
         except Exception:
             traffic = None
     line = {"metric": "MLUPS (two-phase D2Q9)", "value": value, "unit": "MLUPS", "n_gpus": world, "steps": K,
-            "warmup": Wm, "ms_per_step": step_ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "warmup": Wm, "ms_per_step": step_ms, "higher_is_better": True, "scaling": scaling, "vs_baseline": None,
             "dtype": args.dtype, "data": "synthetic",
             "config": {"workload": "synthetic random-block porous medium %dx%d (W x H), fingering_periodic step variant"
                                    % (W, H), "grid_W": W, "grid_H": H, "slab_columns_per_gpu": x1 - x0,

@@ -305,6 +305,27 @@ __global__ void __launch_bounds__(TY, sizeof(T) == 8 ? FDLBM_FUSED_MINB64 : FDLB
     cp_async_wait<0>();
 }
 
+// Column chunk length for `nyt` strips on `n_cta` resident CTA slots.  With c chunks per strip the kernel takes
+// ceil(nyt*c / n_cta) waves of Wl/c columns each; pick the c that minimises waves/c (one wave when the strips
+// divide the slots well, a few shorter waves for tall grids), keeping chunks long enough (>= 96 columns) to
+// amortise the 3-column pipeline warm-up.
+inline int fused_chunk(int nyt, int n_cta, int Wl)
+{
+    int best_c = 1;
+    double best = 1e30;
+    const int c_max = Wl / 96 > 1 ? Wl / 96 : 1;
+    for (int c = 1; c <= c_max && c <= 4096; ++c) {
+        const int waves = (nyt * c + n_cta - 1) / n_cta;
+        const double cost = (double)waves / c * (1.0 + 3.0 * c / Wl);
+        if (cost < best * 0.97) {  // prefer fewer, longer chunks (one lock-step wave) unless clearly better
+            best = cost;
+            best_c = c;
+        }
+    }
+    int chunk = (Wl + best_c - 1) / best_c;
+    return chunk < 8 ? 8 : chunk;
+}
+
 // returns 0 or a cudaError_t
 template <typename T>
 int launch_fused(const LbmParams<T> &P, cudaStream_t stream)
@@ -325,13 +346,10 @@ int launch_fused(const LbmParams<T> &P, cudaStream_t stream)
         if (occ < 1) occ = 1;
         n_cta = sms * occ;
     }
-    // one resident wave: (CTA slots / strips) column chunks per strip, all strips in step
+    // column chunks per strip, all strips of a chunk in step (strips are the fast CTA index)
     const int nyt = (P.H + FUSED_TY - 1) / FUSED_TY;
-    int nchunks = n_cta / nyt;
-    if (nchunks < 1) nchunks = 1;
-    int chunk = (P.Wl + nchunks - 1) / nchunks;
-    if (chunk < 8) chunk = 8;
-    nchunks = (P.Wl + chunk - 1) / chunk;
+    const int chunk = fused_chunk(nyt, n_cta, P.Wl);
+    const int nchunks = (P.Wl + chunk - 1) / chunk;
     kern<<<nyt * nchunks, FUSED_TY, C::SMEM, stream>>>(P, nyt, chunk);
     return 0;
 }

@@ -255,11 +255,8 @@ int launch_fused_vec(const LbmParams<T> &P, cudaStream_t stream)
         n_cta = sms * occ;
     }
     const int nyt = (P.H + C::ROWS - 1) / C::ROWS;
-    int nchunks = n_cta / nyt;
-    if (nchunks < 1) nchunks = 1;
-    int chunk = (P.Wl + nchunks - 1) / nchunks;
-    if (chunk < 8) chunk = 8;
-    nchunks = (P.Wl + chunk - 1) / chunk;
+    const int chunk = fused_chunk(nyt, n_cta, P.Wl);
+    const int nchunks = (P.Wl + chunk - 1) / chunk;
     kern<<<nyt * nchunks, NT, C::SMEM, stream>>>(P, nyt, chunk);
     return 0;
 }
