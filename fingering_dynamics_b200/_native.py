@@ -67,6 +67,11 @@ class Halo(ctypes.Structure):
                 ("recv_hi", ctypes.c_void_p), ("bytes", ctypes.c_size_t)]
 
 
+class AlgebraOut(ctypes.Structure):
+    """fdlbm_algebra_out of include/fdlbm.h"""
+    _fields_ = [(n, ctypes.c_void_p) for n in ("p", "mu", "mix_tau", "a0", "a1_8", "b0", "b1_8")]
+
+
 class PeerInfo(ctypes.Structure):
     """fdlbm_peer_info of include/fdlbm.h (plain bytes: can be pickled and sent to another rank)"""
     _fields_ = [("pid", ctypes.c_int64), ("device", ctypes.c_int32), ("Wl", ctypes.c_int32), ("Hp", ctypes.c_int32),
@@ -106,6 +111,7 @@ _SIGS = {
     "fdlbm_op_collide": (ctypes.c_int, [ctypes.POINTER(Config), ctypes.c_void_p, ctypes.POINTER(Fields)]),
     "fdlbm_op_collision_terms": (ctypes.c_int, [ctypes.POINTER(Config), ctypes.c_void_p, ctypes.POINTER(Fields),
                                                 ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p]),
+    "fdlbm_op_algebra": (ctypes.c_int, [ctypes.POINTER(Config), ctypes.POINTER(Fields), ctypes.POINTER(AlgebraOut)]),
     "fdlbm_op_zou_he": (ctypes.c_int, [ctypes.POINTER(Config), ctypes.POINTER(Fields)]),
     "fdlbm_op_moments": (ctypes.c_int, [ctypes.POINTER(Config), ctypes.c_void_p, ctypes.POINTER(Fields)]),
 }

@@ -161,6 +161,27 @@ __global__ void __launch_bounds__(TPB) k_op_terms(const __grid_constant__ LbmPar
     }
 }
 
+// point-wise getters of Compute on full grids; outputs are the 7 planes of `out` (FieldPtrs reused:
+// rho->p, ux->mu, uy->mix_tau, p->a0, mu->a1_8, mix_tau->b0, gx->b1_8); inputs: psi, and in.{rho,mu,p,lap}
+template <typename T>
+__global__ void __launch_bounds__(TPB) k_op_algebra(const __grid_constant__ LbmParams<T> P, const T *psi_, const T *rho_,
+                                                    const T *mu_, const T *p_, const T *lap_, FieldPtrs<T> out)
+{
+    const int y = blockIdx.x * TPB + threadIdx.x, xl = blockIdx.y;
+    if (y >= P.H) return;
+    const size_t c = cell_idx(P.Hp, xl, y);
+    const T psi = psi_[c], rho = rho_[c], mu = mu_[c], p = p_[c], lap = lap_[c];
+    const T w0 = T(4) / T(9), c0 = T(5) / T(3);
+    out.rho[c] = rho * (T(1) / T(3)) + psi * mu;                       // getP
+    out.ux[c] = chem_potential(P, psi, lap);                            // getMu_plain
+    const T D = (T(1) - psi) + P.M * (T(1) + psi);
+    out.uy[c] = P.eta6m / (rho * D) + T(0.5);                           // getMix_tau
+    out.p[c] = (rho - c0 * p) / w0;                                     // getA0
+    out.mu[c] = T(3) * p;                                               // getA1_8
+    out.mix_tau[c] = (psi - c0 * P.gamma * mu) / w0;                    // getB0
+    out.gx[c] = T(3) * P.gamma * mu;                                    // getB1_8
+}
+
 }  // namespace fdlbm
 
 namespace {
@@ -317,6 +338,35 @@ int fdlbm_op_collision_terms(const fdlbm_config *cfg, const uint8_t *solid, cons
     CU(cudaGetLastError());
     if ((rc = download_pops(e, 0, feq, geq))) return rc;
     return download_pops(e, 1, F, nullptr);
+}
+
+int fdlbm_op_algebra(const fdlbm_config *cfg, const fdlbm_fields *in, const fdlbm_algebra_out *out)
+{
+    if (!cfg || !in || !out || !in->psi || !in->rho) return fail(FDLBM_E_ARG, "null argument (psi and rho are required)");
+    TempEngine t;
+    int rc = op_engine(t, cfg, 0, 0, false);
+    if (rc) return rc;
+    fdlbm_engine *e = t.e;
+    if ((rc = upload_solid(e, nullptr))) return rc;
+    if ((rc = ensure_fields(e))) return rc;
+    const size_t Hp = e->Hp, n = e->plane_elems();
+    const int W = e->cfg.W;
+    // inputs into the two lattices (used as plain scratch planes): psi, rho, mu, p, lap
+    double *scratch = (double *)e->lat[0];
+    CU(cudaMemsetAsync(scratch, 0, 5 * n * sizeof(double), e->stream));
+    const double *ins[5] = {in->psi, in->rho, in->mu, in->p, in->nabla_psi2};
+    for (int k = 0; k < 5; ++k)
+        if (ins[k] && (rc = upload_planes<double>(e, ins[k], 1, 0, W, scratch + k * n, 0, Hp))) return rc;
+    LbmParams<double> P = make_params<double>(e, 0, 0);
+    FieldPtrs<double> F = field_ptrs<double>(e);
+    k_op_algebra<double><<<cell_grid(e, e->Wl), TPB, 0, e->stream>>>(P, scratch, scratch + n, scratch + 2 * n, scratch + 3 * n,
+                                                                      scratch + 4 * n, F);
+    CU(cudaGetLastError());
+    double *dsts[7] = {out->p, out->mu, out->mix_tau, out->a0, out->a1_8, out->b0, out->b1_8};
+    double *srcs[7] = {F.rho, F.ux, F.uy, F.p, F.mu, F.mix_tau, F.gx};
+    for (int k = 0; k < 7; ++k)
+        if ((rc = download_planes<double>(e, dsts[k], 1, 0, W, srcs[k], 0, Hp))) return rc;
+    return drain_transfers(e);
 }
 
 int fdlbm_op_zou_he(const fdlbm_config *cfg, const fdlbm_fields *io)

@@ -195,13 +195,24 @@ class ComputeBase:
         f, g = self._zou_he()
         self.f[:, :, -1], self.g[:, :, -1] = f[:, :, -1], g[:, :, -1]
 
-    # -- simple algebra on stored arrays (the reference's one-liners) ------------------------------------
+    # -- the reference's point-wise getters, evaluated on the GPU (fdlbm_op_algebra) -------------------------
+    def _algebra(self, *names):
+        m = self._m
+        F, hold = self._fields()
+        out = nat.AlgebraOut()
+        res = {}
+        for k in names:
+            res[k] = np.zeros((m.H, m.W))
+            setattr(out, k, res[k].ctypes.data)
+        c = self._cfg()
+        nat.check(nat.lib().fdlbm_op_algebra(ctypes.byref(c), ctypes.byref(F), ctypes.byref(out)))
+        return res
+
     def getP(self):
-        return 1 / 3 * self.rho + self._masked(np.asarray(self.psi)) * self.mu
+        return self._masked(self._algebra("p")["p"])
 
     def getMu_plain(self):
-        m = self._m
-        return m.a * self.psi * (1.0 - self.psi ** 2) * self.A_SIGN - m.kappa * self.nabla_psi2
+        return self._algebra("mu")["mu"]
 
     def getMu(self):
         return self._masked(self.getMu_plain())
@@ -213,23 +224,19 @@ class ComputeBase:
         return self._masked(self._moments()["uy"])
 
     def getMix_tau(self):
-        m = self._m
-        v1 = m.Eta_n / self.rho
-        v2 = m.Eta_n * m.M / self.rho
-        psi = self._masked(np.asarray(self.psi))
-        return 3 * (2 * v1 * v2 / (v1 * (1.0 - psi) + v2 * (1.0 + psi))) + 0.5
+        return self._masked(self._algebra("mix_tau")["mix_tau"])
 
     def getA0(self):
-        return (self.rho - 3.0 * (1.0 - self.w[0]) * self.p) / self.w[0]
+        return self._masked(self._algebra("a0")["a0"])
 
     def getA1_8(self):
-        return 3 * self.p
+        return self._masked(self._algebra("a1_8")["a1_8"])
 
     def getB0(self):
-        return (self._masked(np.asarray(self.psi)) - 3.0 * (1.0 - self.w[0]) * self.gamma * self.mu) / self.w[0]
+        return self._masked(self._algebra("b0")["b0"])
 
     def getB1_8(self):
-        return 3 * self.gamma * self.mu
+        return self._masked(self._algebra("b1_8")["b1_8"])
 
     # -- the whole loop on the device ----------------------------------------------------------------------
     def make_engine(self, reflect, dtype="f64", **kw):

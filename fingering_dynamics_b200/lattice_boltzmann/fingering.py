@@ -76,7 +76,7 @@ class Compute(ComputeBase):
         self.nabla_psix, self.nabla_psiy, self.nabla_psi2 = self._stencils()
         self.p = self.getP()
         self.mu = self.getMu()
-        self.uy = (np.zeros(n) + self.mu * self.nabla_psiy[self.mask] / 2) / self.rho
+        self.uy = self.mu * self.nabla_psiy[self.mask] / 2 / self.rho  # getUy with f = 0 (fingering.py:123,140-145)
         self.mix_tau = self.getMix_tau()
         feq, geq, F = self._terms()
         self.feq = np.array([feq[i][self.mask] for i in range(9)])

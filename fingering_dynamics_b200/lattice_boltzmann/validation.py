@@ -82,9 +82,6 @@ class Compute(ComputeBase):
         self.feq, self.geq = feq, geq
         self.f, self.g = feq.copy(), geq.copy()
 
-    def getP(self):
-        return (cs ** 2) * self.rho + self.psi * self.mu
-
     def updateP(self):
         self.p = self.getP()
 

@@ -170,6 +170,14 @@ int fdlbm_op_collide(const fdlbm_config *cfg, const uint8_t *solid, const fdlbm_
  * macroscopic arrays in `in`; feq, geq, F are (9,H,W) outputs (zero on solid cells), any may be NULL */
 int fdlbm_op_collision_terms(const fdlbm_config *cfg, const uint8_t *solid, const fdlbm_fields *in, double *feq,
                              double *geq, double *F);
+/* The point-wise getters of Compute from the arrays in `in` (psi, rho, mu, nabla_psi2), each output (H,W), any
+ * may be NULL: p = getP (fingering_periodic.py:123-124, uses in->mu), mu = getMu_plain (:146-149, uses
+ * in->nabla_psi2), mix_tau = getMix_tau (:201-208), a0/a1_8/b0/b1_8 = getA0/getA1_8/getB0/getB1_8 (:155-169,
+ * use in->p and in->mu). */
+typedef struct {
+    double *p, *mu, *mix_tau, *a0, *a1_8, *b0, *b1_8;
+} fdlbm_algebra_out;
+int fdlbm_op_algebra(const fdlbm_config *cfg, const fdlbm_fields *in, const fdlbm_algebra_out *out);
 /* zou_he_boundary_inlet + _outlet (fingering_periodic.py:268-324 / fingering.py:298-390), in place */
 int fdlbm_op_zou_he(const fdlbm_config *cfg, const fdlbm_fields *io);
 /* the moment updates of one iteration (fingering_periodic.py:470-479): f,g in; all fields out */
