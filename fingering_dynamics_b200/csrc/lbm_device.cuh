@@ -70,9 +70,11 @@ static_assert(opp(5) == 7 && opp(6) == 8 && opp(7) == 5 && opp(8) == 6, "diagona
 // v_i <- src_i(x - e_i) with wrap in y (x wraps through the ghost columns), then for every set
 // reflect bit v_i <- src_opp(i)(x)  [fingering_periodic.py:327-343 + bounce_back.py:89-167].
 template <typename T>
-__device__ __forceinline__ void pull(const LbmParams<T> &P, int xl, int y, int base, unsigned bits, T v[9])
+__device__ __forceinline__ void pull_hp(const LbmParams<T> &P, int Hp, int xl, int y, int base, unsigned bits, T v[9])
 {
-    const int H = P.H, Hp = P.Hp;
+    // Hp is passed separately: when the caller knows it at compile time every population offset below
+    // folds into the load's immediate field
+    const int H = P.H;
     int ym = y - 1;
     if (ym < 0) ym += H;
     int yp = y + 1;
@@ -117,6 +119,12 @@ __device__ __forceinline__ void pull(const LbmParams<T> &P, int xl, int y, int b
     v[7] = *s7;
     v[8] = *s8;
 #endif
+}
+
+template <typename T>
+__device__ __forceinline__ void pull(const LbmParams<T> &P, int xl, int y, int base, unsigned bits, T v[9])
+{
+    pull_hp(P, P.Hp, xl, y, base, bits, v);
 }
 
 // Zou-He rules for g on the faces (fingering_periodic.py:278-324, fingering.py:305-390).
@@ -381,12 +389,18 @@ __device__ __forceinline__ void store_cell_at(T *lat, int Hp, int xl, int y, con
 }
 
 template <typename T>
+__device__ __forceinline__ void store_cell_hp(const LbmParams<T> &P, int Hp, int xl, int y, const T f[9], const T g[9])
+{
+    store_cell_at(P.dst, Hp, xl, y, f, g);
+    // halo push: the two edge columns also land in the neighbours' ghost columns (peer stores over NVLink)
+    if (P.peer_lo && xl < G) store_cell_at(P.peer_lo, Hp, P.peer_lo_Wl + xl, y, f, g);
+    if (P.peer_hi && xl >= P.Wl - G) store_cell_at(P.peer_hi, Hp, xl - P.Wl, y, f, g);
+}
+
+template <typename T>
 __device__ __forceinline__ void store_cell(const LbmParams<T> &P, int xl, int y, const T f[9], const T g[9])
 {
-    store_cell_at(P.dst, P.Hp, xl, y, f, g);
-    // halo push: the two edge columns also land in the neighbours' ghost columns (peer stores over NVLink)
-    if (P.peer_lo && xl < G) store_cell_at(P.peer_lo, P.Hp, P.peer_lo_Wl + xl, y, f, g);
-    if (P.peer_hi && xl >= P.Wl - G) store_cell_at(P.peer_hi, P.Hp, xl - P.Wl, y, f, g);
+    store_cell_hp(P, P.Hp, xl, y, f, g);
 }
 
 }  // namespace fdlbm

@@ -135,7 +135,9 @@ struct RawFlags {
     unsigned refl, word;  // reflect byte and solid-mask word exactly as loaded
 };
 
-template <typename T, int TY, bool STAGE_F>
+// HPC > 0: the row pitch Hp is the compile-time constant HPC (all population offsets become immediates of the
+// loads / stores / cp.async); HPC == 0: Hp is read from the parameters (any grid height).
+template <typename T, int TY, bool STAGE_F, int HPC>
 __global__ void __launch_bounds__(TY, sizeof(T) == 8 ? FDLBM_FUSED_MINB64 : FDLBM_FUSED_MINB32) k_fused(const __grid_constant__ LbmParams<T> P, int nyt, int chunk)
 {
     using C = FusedCfg<T, TY, STAGE_F>;
@@ -145,7 +147,7 @@ __global__ void __launch_bounds__(TY, sizeof(T) == 8 ? FDLBM_FUSED_MINB64 : FDLB
     T *gst = reinterpret_cast<T *>(smem_raw);        // [NS][9][PT]
     T *fst = gst + NS * FAM;                         // [NS][9][PT] when STAGE_F
     const int t = threadIdx.x, lane = t & 31;
-    const int H = P.H, Hp = P.Hp;
+    const int H = P.H, Hp = HPC > 0 ? HPC : P.Hp;
 
     const int yt = blockIdx.x % nyt;
     const int xs = (blockIdx.x / nyt) * chunk;
@@ -258,7 +260,7 @@ __global__ void __launch_bounds__(TY, sizeof(T) == 8 ? FDLBM_FUSED_MINB64 : FDLB
         T f[9];
         if (!STAGE_F) {
             // f of column x straight into registers; consumed after the psi phase below
-            if (active) pull(P, x, y, 0, fl_cur & 0xffu, f);
+            if (active) pull_hp(P, Hp, x, y, 0, fl_cur & 0xffu, f);
             // and the lines of f column x+L2_AHEAD into L2: one prefetch per 128-byte line of the strip
             constexpr int LPP = (TY * (int)sizeof(T) + 127) / 128;  // lines per population row
             const int cf = x + FUSED_L2_AHEAD;
@@ -288,7 +290,7 @@ __global__ void __launch_bounds__(TY, sizeof(T) == 8 ? FDLBM_FUSED_MINB64 : FDLB
                 moments(P, f, p0_0, gx, gy, lap, m);
                 collide(P, m, f, g_cur);
             }
-            store_cell(P, x, y, f, g_cur);
+            store_cell_hp(P, Hp, x, y, f, g_cur);
             if (P.zou_he) {  // the next step's Zou-He needs grad psi and mu at the face columns
                 const int gx_ = P.gx0 + x;
                 if (gx_ < 2 || gx_ >= P.W - 2) P.psi_new[cell_idx(Hp, x, y)] = p0_0;
@@ -327,11 +329,11 @@ inline int fused_chunk(int nyt, int n_cta, int Wl)
 }
 
 // returns 0 or a cudaError_t
-template <typename T>
-int launch_fused(const LbmParams<T> &P, cudaStream_t stream)
+template <typename T, int HPC>
+int launch_fused_hp(const LbmParams<T> &P, cudaStream_t stream)
 {
     using C = FusedCfg<T, FUSED_TY, FUSED_STAGE_F>;
-    auto kern = k_fused<T, FUSED_TY, FUSED_STAGE_F>;
+    auto kern = k_fused<T, FUSED_TY, FUSED_STAGE_F, HPC>;
     static int n_cta = 0;  // per instantiation; device properties do not change within a process
     if (n_cta == 0) {
         int dev = 0, sms = 0, occ = 0;
@@ -352,6 +354,21 @@ int launch_fused(const LbmParams<T> &P, cudaStream_t stream)
     const int nchunks = (P.Wl + chunk - 1) / chunk;
     kern<<<nyt * nchunks, FUSED_TY, C::SMEM, stream>>>(P, nyt, chunk);
     return 0;
+}
+
+// the common row pitches get a kernel with Hp folded into the instruction immediates
+template <typename T>
+int launch_fused(const LbmParams<T> &P, cudaStream_t stream)
+{
+#ifdef FDLBM_HP_SPECIALISATION  // measured on B200: no gain (19.88 vs 19.93 GLUPS), so off by default
+    switch (P.Hp) {
+    case 2048: return launch_fused_hp<T, 2048>(P, stream);
+    case 4096: return launch_fused_hp<T, 4096>(P, stream);
+    case 8192: return launch_fused_hp<T, 8192>(P, stream);
+    default: break;
+    }
+#endif
+    return launch_fused_hp<T, 0>(P, stream);
 }
 
 }  // namespace fdlbm
