@@ -131,33 +131,33 @@ __device__ __forceinline__ void pull(const LbmParams<T> &P, int xl, int y, int b
 template <typename T>
 __device__ __forceinline__ void zou_he_g(const LbmParams<T> &P, int gx, int y, T g[9])
 {
-    const T w1 = T(1) / T(9), w5 = T(1) / T(36);
-    const T den = w1 + w5 + w5;
+    // weight ratios of the reference's rules: w1/(w1+w5+w8) = 2/3, w5/(w1+w5+w8) = 1/6, w6/(w6+w8) = 1/2
+    const T r1 = T(2) / T(3), r5 = T(1) / T(6);
     if (gx == 0) {
         const bool fg = P.zou_he == 2;
         if (fg && y == 0) {  // fingering.py:336-348
             g[1] = g[3];
             g[2] = g[4];
             g[5] = g[7];
-            g[6] = w5 * (T(1) - (g[0] + g[1] + g[2] + g[3] + g[4] + g[5] + g[7])) / (w5 + w5);
+            g[6] = T(0.5) * (T(1) - (g[0] + g[1] + g[2] + g[3] + g[4] + g[5] + g[7]));
             g[8] = g[6];
         } else if (fg && y == P.H - 1) {  // fingering.py:352-364
             g[1] = g[3];
             g[4] = g[2];
             g[8] = g[6];
-            g[5] = w5 * (T(1) - (g[0] + g[1] + g[2] + g[3] + g[4] + g[6] + g[8])) / (w5 + w5);
+            g[5] = T(0.5) * (T(1) - (g[0] + g[1] + g[2] + g[3] + g[4] + g[6] + g[8]));
             g[7] = g[5];
         } else {
             const T psi_in = P.psi_left - (g[0] + g[2] + g[3] + g[4] + g[6] + g[7]);
-            g[1] = w1 * psi_in / den;
-            g[5] = w5 * psi_in / den;
+            g[1] = r1 * psi_in;
+            g[5] = r5 * psi_in;
             g[8] = g[5];
         }
     }
     if (gx == P.W - 1) {
         const T psi_out = P.psi_right - (g[0] + g[1] + g[2] + g[4] + g[5] + g[8]);
-        g[3] = w1 * psi_out / den;
-        g[6] = w5 * psi_out / den;
+        g[3] = r1 * psi_out;
+        g[6] = r5 * psi_out;
         g[7] = g[6];
         if (P.zou_he == 2) {  // fingering.py:387-390
             if (y == 0) g[2] = g[4];
@@ -306,6 +306,13 @@ __device__ __forceinline__ void stream_bc_f(const LbmParams<T> &P, int xl, int y
     }
 }
 
+__device__ __forceinline__ double rcp_exact(double x) { return 1.0 / x; }
+#ifdef FDLBM_F32_IEEE_DIV
+__device__ __forceinline__ float rcp_exact(float x) { return 1.0f / x; }
+#else
+__device__ __forceinline__ float rcp_exact(float x) { return __frcp_rn(x); }
+#endif
+
 // Macroscopic moments of one fluid cell (fingering_periodic.py:123-152, 201-208).
 template <typename T>
 struct Macro {
@@ -328,8 +335,9 @@ __device__ __forceinline__ void moments(const LbmParams<T> &P, const T f[9], T p
     const T D = (T(1) - psi) + P.M * (T(1) + psi);
     const T rD = m.rho * D;
     const T X = P.eta6m + T(0.5) * rD;
-    // (IEEE division: a MUFU.RCP64H seed + Newton steps by hand measured 2-12 % SLOWER on B200, A/B in one run)
-    const T r = T(1) / (m.rho * X);
+    // fp64: IEEE division (a MUFU.RCP64H seed + Newton steps by hand measured 2-12 % SLOWER on B200, A/B in one
+    // run); fp32: correctly rounded reciprocal without the division's slow-path call
+    const T r = rcp_exact(m.rho * X);
     const T inv_rho = r * X;
     m.inv_mt = rD * m.rho * r;
     m.ux = (jx + T(0.5) * m.mu * gx) * inv_rho;
