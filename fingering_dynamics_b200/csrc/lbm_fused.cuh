@@ -210,13 +210,13 @@ __global__ void __launch_bounds__(TY, sizeof(T) == 8 ? FDLBM_FUSED_MINB64 : FDLB
         return (((g[0] + g[1]) + (g[2] + g[3])) + ((g[4] + g[5]) + (g[6] + g[7]))) + g[8];
     };
     // psi_new of column c on rows y-1, y, y+1 (q_m, q_0, q_p); the pulled g of the own cell is returned
-    auto psi_column = [&](int c, unsigned fl_own, RawFlags fl_edge, T g[9], T &q_m, T &q_0, T &q_p) {
+    auto psi_column = [&](int c, unsigned fl_own, unsigned fl_edge, T g[9], T &q_m, T &q_0, T &q_p) {
         q_0 = T(0);
         if (active) q_0 = psi_staged(c, y, j, fl_own, g);
         T e1 = T(0), e2 = T(0);
         if (edge) {
             T gh[9];
-            e1 = psi_staged(c, ye1, je1, decode(fl_edge, ye1), gh);
+            e1 = psi_staged(c, ye1, je1, fl_edge, gh);
             if (edge2) e2 = psi_staged(c, ye2, je2, decode(load_flags(c, ye2), ye2), gh);
         }
         const T dn = __shfl_up_sync(FULL, q_0, 1), up = __shfl_down_sync(FULL, q_0, 1);
@@ -245,17 +245,23 @@ __global__ void __launch_bounds__(TY, sizeof(T) == 8 ? FDLBM_FUSED_MINB64 : FDLB
     }
     cp_async_wait<D>();  // g columns <= xs have landed (this thread's share)
     __syncthreads();
-    psi_column(xs - 1, decode(rf_m1, y), re_m1, g_nxt, pm_m, pm_0, pm_p);
+    psi_column(xs - 1, decode(rf_m1, y), decode(re_m1, ye1), g_nxt, pm_m, pm_0, pm_p);
     __syncthreads();
     prefetch(xs - 1);
     cp_async_wait<D>();  // g column xs+1 has landed
     __syncthreads();
     fl_cur = decode(rf_0, y);
-    psi_column(xs, fl_cur, re_0, g_cur, p0_m, p0_0, p0_p);
+    psi_column(xs, fl_cur, decode(re_0, ye1), g_cur, p0_m, p0_0, p0_p);
 
     for (int x = xs; x < xe; ++x) {
         cp_async_wait<D - 1>();  // g column x+2 (and staged f column x+1) have landed
         __syncthreads();         // ... for every thread; and everybody is done with iteration x-1
+        // Decode the flags of column x+1 BEFORE any new global load is issued: they were loaded two iterations
+        // ago, but the hardware scoreboard slots are shared -- decoding them after this iteration's f loads
+        // would wait for those loads too (measured: 18 % of all stall samples on the first psi shuffle).
+        fl_nxt = decode(fq0, y);
+        unsigned fe_nxt = decode(eq0, ye1);
+        asm volatile("" : "+r"(fl_nxt), "+r"(fe_nxt)::"memory");
         prefetch(x);             // overwrites the stage of g column x-1 (f column x-2): no longer read
         T f[9];
         if (!STAGE_F) {
@@ -273,8 +279,7 @@ __global__ void __launch_bounds__(TY, sizeof(T) == 8 ? FDLBM_FUSED_MINB64 : FDLB
         }
         const RawFlags fq2 = active ? load_flags(x + 3, y) : z;  // decoded two iterations from now
         const RawFlags eq2 = edge ? load_flags(x + 3, ye1) : z;
-        fl_nxt = decode(fq0, y);
-        psi_column(x + 1, fl_nxt, eq0, g_nxt, pp_m, pp_0, pp_p);
+        psi_column(x + 1, fl_nxt, fe_nxt, g_nxt, pp_m, pp_0, pp_p);
         if (active) {
             if (STAGE_F)
                 pull_staged<T, PT>(fst + slot(x - 1) * FAM, fst + slot(x) * FAM, fst + slot(x + 1) * FAM, j, fl_cur & 0xffu, f);

@@ -101,19 +101,19 @@ __global__ void __launch_bounds__(NT, sizeof(T) == 8 ? FDLBM_FUSED_MINB64 : FDLB
         return (((g[0] + g[1]) + (g[2] + g[3])) + ((g[4] + g[5]) + (g[6] + g[7]))) + g[8];
     };
     // psi_new of column c on the thread's rows (q[0..VEC-1]) and its outer neighbours (q_lo, q_hi); pulled g returned
-    auto psi_column = [&](int c, RawFlags fl_own, RawFlags fl_lo, RawFlags fl_hi, unsigned fl[VEC], T g[VEC][9], T q[VEC],
-                          T &q_lo, T &q_hi) {
+    // (flags arrive DECODED: fl[] own rows, fl_lo / fl_hi the outer neighbours)
+    auto psi_column = [&](int c, unsigned fl_lo, unsigned fl_hi, const unsigned fl[VEC], T g[VEC][9], T q[VEC], T &q_lo,
+                          T &q_hi) {
 #pragma unroll
         for (int v = 0; v < VEC; ++v) {
             q[v] = T(0);
-            fl[v] = decode(fl_own, yb, v);
             if (v < nv) q[v] = psi_staged(c, yb + v, jb + v, fl[v], g[v]);
         }
         T e_lo = T(0), e_hi = T(0);
         if (edge_lo || edge_hi) {
             T gh[9];
-            if (edge_lo) e_lo = psi_staged(c, ye_lo, jb - 1, decode(fl_lo, ye_lo, 0), gh);
-            if (edge_hi) e_hi = psi_staged(c, ye_hi, jb + nv, decode(fl_hi, ye_hi, 0), gh);
+            if (edge_lo) e_lo = psi_staged(c, ye_lo, jb - 1, fl_lo, gh);
+            if (edge_hi) e_hi = psi_staged(c, ye_hi, jb + nv, fl_hi, gh);
         }
         const T dn = __shfl_up_sync(FULL, q[VEC - 1], 1), up = __shfl_down_sync(FULL, q[0], 1);
         q_lo = edge_lo ? e_lo : dn;
@@ -144,16 +144,28 @@ __global__ void __launch_bounds__(NT, sizeof(T) == 8 ? FDLBM_FUSED_MINB64 : FDLB
     }
     cp_async_wait<D>();
     __syncthreads();
-    psi_column(xs - 1, rf_m1, rl_m1, rh_m1, fl_nxt, g_nxt, pm, pm_lo, pm_hi);
+#pragma unroll
+    for (int v = 0; v < VEC; ++v) fl_nxt[v] = decode(rf_m1, yb, v);
+    psi_column(xs - 1, decode(rl_m1, ye_lo, 0), decode(rh_m1, ye_hi, 0), fl_nxt, g_nxt, pm, pm_lo, pm_hi);
     __syncthreads();
     prefetch(xs - 1);
     cp_async_wait<D>();
     __syncthreads();
-    psi_column(xs, rf_0, rl_0, rh_0, fl_cur, g_cur, p0, p0_lo, p0_hi);
+#pragma unroll
+    for (int v = 0; v < VEC; ++v) fl_cur[v] = decode(rf_0, yb, v);
+    psi_column(xs, decode(rl_0, ye_lo, 0), decode(rh_0, ye_hi, 0), fl_cur, g_cur, p0, p0_lo, p0_hi);
 
     for (int x = xs; x < xe; ++x) {
         cp_async_wait<D - 1>();  // g column x+2 has landed
         __syncthreads();         // ... for every thread; and everybody is done with iteration x-1
+        // decode the flags of column x+1 before any new global load is issued (see k_fused)
+        unsigned fl_lo_n = decode(lq0, ye_lo, 0), fl_hi_n = decode(hq0, ye_hi, 0);
+#pragma unroll
+        for (int v = 0; v < VEC; ++v) {
+            fl_nxt[v] = decode(fq0, yb, v);
+            asm volatile("" : "+r"(fl_nxt[v]));
+        }
+        asm volatile("" : "+r"(fl_lo_n), "+r"(fl_hi_n)::"memory");
         prefetch(x);
         T f[VEC][9];
 #pragma unroll
@@ -172,7 +184,7 @@ __global__ void __launch_bounds__(NT, sizeof(T) == 8 ? FDLBM_FUSED_MINB64 : FDLB
         const RawFlags fq2 = load_flags(x + 3, yb, nv);
         const RawFlags lq2 = edge_lo ? load_flags(x + 3, ye_lo, 1) : z;
         const RawFlags hq2 = edge_hi ? load_flags(x + 3, ye_hi, 1) : z;
-        psi_column(x + 1, fq0, lq0, hq0, fl_nxt, g_nxt, pp, pp_lo, pp_hi);
+        psi_column(x + 1, fl_lo_n, fl_hi_n, fl_nxt, g_nxt, pp, pp_lo, pp_hi);
 
         const int gx_ = P.gx0 + x;
         const bool face = P.zou_he && (gx_ == 0 || gx_ == P.W - 1);
