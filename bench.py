@@ -46,10 +46,14 @@ class ClockSampler:
     def __init__(self, index=0):
         self.rows, self.proc, self.index = [], None, index
         self.t_mark = None
+        self.t_end = None
 
     def mark(self):
         """start of the timed region: only samples taken after this call are summarised"""
         self.t_mark = time.time()
+
+    def end(self):
+        self.t_end = time.time()
 
     def __enter__(self):
         try:
@@ -75,9 +79,10 @@ class ClockSampler:
     def summary(self):
         sm, mx, reasons = [], [], set()
         names = ("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap")
-        rows = [r for (ts, r) in self.rows if self.t_mark is None or ts >= self.t_mark]
-        if len(rows) < 3:
-            rows = [r for (ts, r) in self.rows][-5:]
+        t1 = (self.t_end + 0.1) if self.t_end else float("inf")
+        rows = [r for (ts, r) in self.rows if (self.t_mark is None or ts >= self.t_mark) and ts <= t1]
+        if len(rows) < 3:  # short timed region: the samples closest to it (warm-up is load too)
+            rows = [r for (ts, r) in self.rows if ts <= t1][-5:]
         for r in rows:
             try:
                 sm.append(float(r[0]))
@@ -165,6 +170,8 @@ def main():
     if world != args.gpus and world > 1:
         raise SystemExit("--gpus %d but WORLD_SIZE=%d" % (args.gpus, world))
     torch.cuda.set_device(local)
+    clocks = ClockSampler(local)   # nvidia-smi takes a moment to start: launch it before the host-side set-up
+    clocks.__enter__()
     if world > 1:
         import torch.distributed as dist
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
@@ -223,15 +230,16 @@ def main():
     # ---- device-resident throughput ("value") -------------------------------------------------------
     runner.set_state(col0=x0, **st)
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    with ClockSampler(local) as clocks:   # nvidia-smi needs a moment to start: launch it before the warm-up
-        runner.step(Wm)
-        barrier()
-        l0 = eng.launch_count
-        clocks.mark()
-        ev0.record(stream)
-        runner.step(K)
-        ev1.record(stream)
-        barrier()
+    runner.step(Wm)
+    barrier()
+    l0 = eng.launch_count
+    clocks.mark()
+    ev0.record(stream)
+    runner.step(K)
+    ev1.record(stream)
+    barrier()
+    clocks.end()
+    clocks.__exit__()
     ms = ev0.elapsed_time(ev1)
     launches = eng.launch_count - l0
     if world > 1:
