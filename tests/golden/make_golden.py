@@ -421,6 +421,7 @@ if __name__ == "__main__":
     ap = argparse.ArgumentParser()
     ap.add_argument("--full", action="store_true", help="also run config 1 at 400x400 for 1000 steps (~3 min)")
     ap.add_argument("--only", default="")
+    ap.add_argument("--full23", action="store_true", help="configs 2 and 3 at their shipped sizes (~2 min)")
     args = ap.parse_args()
     np.seterr(all="raise")  # the reference's own failure detection (fingering_periodic.py:497)
     todo = {"fp": make_fp_small, "fg": make_fg_small,
@@ -431,3 +432,70 @@ if __name__ == "__main__":
             fn()
     if args.full:
         make_fp_full()
+
+
+# ----------------------------------------------------------------------------------------------
+# configs 2 and 3 at their shipped sizes: scalars + subsampled fields (run with --full)
+# ----------------------------------------------------------------------------------------------
+def make_fg_full():
+    """fingering.py as shipped (380x380, 40 squares, fingering.py:16-50, 534-550), np.random.seed(0)."""
+    H, W = FG.H, FG.W
+    rects, count, flag = [], 1, True
+    while True:
+        if (count + 1) * 20 > 380:
+            break
+        if flag:
+            for i in range(4):
+                rects.append(((count * 20, 60 * (i + 1) + i * 20), ((count + 1) * 20, 60 * (i + 1) + (i + 1) * 20)))
+            flag = False
+            count += 2
+            continue
+        else:
+            for i in range(5):
+                rects.append(((count * 20, 60 * i + (i + 1) * 20), ((count + 1) * 20, 60 * i + (i + 2) * 20)))
+            flag = True
+            count += 2
+    cr = CB.Createblock(H, W)
+    bb = BB.Bounce_back(H, W)
+    block_psi_all, corner_list = cr.setblock(rects)
+    mask = np.logical_not(np.where(block_psi_all == 1, True, False))
+    np.random.seed(0)
+    cm = FG.Compute(mask)
+    d = {"H": H, "W": W, "n_rects": len(rects), "n_fluid": int(mask.sum()), "mask_bits": np.packbits(mask),
+         "rects": np.array([[r[0][0], r[0][1], r[1][0], r[1][1]] for r in rects])}
+    d.update(consts(FG, ["tau", "gamma", "a", "kappa", "Eta_n", "M", "u0", "psi_wall"]))
+    for it in range(1, 301):
+        fg_iteration(cm, mask, bb, corner_list)
+        if it in (10, 100, 300):
+            tag = "s%d" % it
+            d[tag + "_sum_psi"] = np.float64(cm.psi.sum())
+            d[tag + "_sum_rho"] = np.float64(cm.rho.sum())
+            for k in ("rho", "ux", "uy"):
+                d["%s_%s_sub" % (tag, k)] = full(mask, getattr(cm, k))[::5, ::5].copy()
+            d[tag + "_psi_sub"] = cm.psi[::5, ::5].copy()
+            print("fg_full step", it, d[tag + "_sum_psi"], d[tag + "_sum_rho"], flush=True)
+    np.savez_compressed(os.path.join(OUT, "fg_full_scalars.npz"), **d)
+
+
+def make_va_full():
+    """validation.py as shipped (200x250, psi_wall = 0, validation.py:14-40)."""
+    with contextlib.redirect_stdout(io.StringIO()):
+        cm = VA.Compute()
+    d = {"H": VA.H, "W": VA.W}
+    d.update(consts(VA, ["tau", "gamma", "a", "kappa", "Eta_n", "M", "psi_wall", "cs", "c"]))
+    for it in range(1, 501):
+        va_iteration(cm)
+        if it in (10, 100, 500):
+            tag = "s%d" % it
+            d[tag + "_sum_psi"] = np.float64(cm.psi.sum())
+            d[tag + "_sum_rho"] = np.float64(cm.rho.sum())
+            for k in ("psi", "rho", "ux", "uy"):
+                d["%s_%s_sub" % (tag, k)] = np.asarray(getattr(cm, k))[::5, ::5].copy()
+            print("va_full step", it, d[tag + "_sum_psi"], d[tag + "_sum_rho"], flush=True)
+    np.savez_compressed(os.path.join(OUT, "va_full_scalars.npz"), **d)
+
+
+if __name__ == "__main__" and "--full23" in sys.argv:
+    np.seterr(all="raise")
+    make_fg_full()
+    make_va_full()

@@ -123,3 +123,52 @@ def test_fingering_periodic_main_default_geometry(golden):
     assert abs(cm.psi.sum() - float(d["s100_sum_psi"])) <= 1e-10 * abs(float(d["s100_sum_psi"]))
     assert abs(cm.rho.sum() - float(d["s100_sum_rho"])) <= 1e-10 * float(d["s100_sum_rho"])
     assert hp.rel_err(cm.psi[::5, ::5], d["s100_psi_sub"]) <= TOL
+
+
+def test_fingering_shipped_configuration_against_reference_scalars(golden):
+    """config 3 as shipped (fingering.py: 380x380, 40 squares, np.random.seed(0)) for 300 iterations,
+    twin drivers + engine against the reference's own numbers (tests/golden/make_golden.py --full23)."""
+    from fingering_dynamics_b200.lattice_boltzmann import fingering as FG, _compute
+    from fingering_dynamics_b200.lattice_boltzmann.create_block import Createblock
+    d = golden("fg_full_scalars")
+    assert (FG.H, FG.W) == (int(d["H"]), int(d["W"]))
+    rects = FG.default_rectangles()
+    assert np.array_equal(np.array([[r[0][0], r[0][1], r[1][0], r[1][1]] for r in rects]), d["rects"])
+    bpa, corner_list = Createblock(FG.H, FG.W).setblock(rects)
+    mask = np.logical_not(bpa == 1)
+    assert np.array_equal(mask, np.unpackbits(d["mask_bits"])[:FG.H * FG.W].reshape(FG.H, FG.W).astype(bool))
+    np.random.seed(0)
+    cm = FG.Compute(mask)
+    eng = cm.make_engine(FG.reflect_bits(corner_list))
+    done = 0
+    for step in (10, 100, 300):
+        eng.step(step - done)
+        done = step
+        st = eng.get_state(("psi", "rho", "ux", "uy"))
+        tag = "s%d" % step
+        assert abs(st["psi"].sum() - float(d[tag + "_sum_psi"])) <= 1e-10 * abs(float(d[tag + "_sum_psi"]))
+        assert abs(st["rho"][mask].sum() - float(d[tag + "_sum_rho"])) <= 1e-10 * float(d[tag + "_sum_rho"])
+        for k in ("psi", "rho", "ux", "uy"):
+            assert hp.rel_err(st[k][::5, ::5], d["%s_%s_sub" % (tag, k)]) <= TOL, (step, k)
+    eng.close()
+
+
+def test_validation_shipped_configuration_against_reference_scalars(golden):
+    """config 2 as shipped (validation.py: 200x250 droplet, psi_wall = 0) for 500 iterations."""
+    from fingering_dynamics_b200 import geometry as geo
+    from fingering_dynamics_b200.lattice_boltzmann import validation as VA
+    d = golden("va_full_scalars")
+    assert (VA.H, VA.W, VA.psi_wall) == (int(d["H"]), int(d["W"]), float(d["c_psi_wall"]))
+    cm = VA.Compute()
+    eng = cm.make_engine(geo.reflect_bits_wall_rows(VA.H, VA.W, 0, VA.H - 1))
+    done = 0
+    for step in (10, 100, 500):
+        eng.step(step - done)
+        done = step
+        st = eng.get_state(("psi", "rho", "ux", "uy"))
+        tag = "s%d" % step
+        assert abs(st["psi"].sum() - float(d[tag + "_sum_psi"])) <= 1e-10 * abs(float(d[tag + "_sum_psi"]))
+        assert abs(st["rho"].sum() - float(d[tag + "_sum_rho"])) <= 1e-12 * float(d[tag + "_sum_rho"])
+        for k in ("psi", "rho", "ux", "uy"):
+            assert hp.rel_err(st[k][::5, ::5], d["%s_%s_sub" % (tag, k)]) <= TOL, (step, k)
+    eng.close()
