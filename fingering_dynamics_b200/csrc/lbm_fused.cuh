@@ -41,6 +41,9 @@ namespace fdlbm {
 #ifndef FDLBM_STAGE_F
 #define FDLBM_STAGE_F 0
 #endif
+#ifndef FDLBM_BULK_COPY
+#define FDLBM_BULK_COPY 1  // g stages of interior strips through cp.async.bulk + mbarrier (0: per-thread cp.async only)
+#endif
 constexpr int FUSED_TY = FDLBM_FUSED_TY;  // rows per strip = threads per CTA
 constexpr int FUSED_D = FDLBM_FUSED_D;    // cp.async prefetch distance in columns
 constexpr bool FUSED_STAGE_F = FDLBM_STAGE_F != 0;
@@ -66,6 +69,38 @@ __device__ __forceinline__ void cp_async_wait()
     asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory");
 }
 __device__ __forceinline__ void prefetch_l2(const void *p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
+
+// ---- bulk asynchronous copies (the TMA engine's 1-D path, cp.async.bulk) completing on an mbarrier ----------
+__device__ __forceinline__ unsigned smem_u32(const void *p) { return (unsigned)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(void *bar, unsigned count)
+{
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_fence_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void mbar_expect_tx(void *bar, unsigned bytes)
+{
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(void *dst, const void *src, unsigned bytes, void *bar)
+{
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst)),
+                 "l"(src), "r"(bytes), "r"(smem_u32(bar))
+                 : "memory");
+}
+__device__ __forceinline__ void mbar_wait(void *bar, unsigned parity)
+{
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "MBAR_WAIT:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra MBAR_DONE;\n"
+        "bra MBAR_WAIT;\n"
+        "MBAR_DONE:\n"
+        "}\n" ::"r"(smem_u32(bar)),
+        "r"(parity)
+        : "memory");
+}
 
 template <typename T, int TY, bool STAGE_F>
 struct FusedCfg {
@@ -146,6 +181,7 @@ __global__ void __launch_bounds__(TY, sizeof(T) == 8 ? FDLBM_FUSED_MINB64 : FDLB
     extern __shared__ __align__(16) unsigned char smem_raw[];
     T *gst = reinterpret_cast<T *>(smem_raw);        // [NS][9][PT]
     T *fst = gst + NS * FAM;                         // [NS][9][PT] when STAGE_F
+    __shared__ __align__(8) unsigned long long bars[NS];  // one mbarrier per g stage (bulk-copy path)
     const int t = threadIdx.x, lane = t & 31;
     const int H = P.H, Hp = HPC > 0 ? HPC : P.Hp;
 
@@ -174,14 +210,43 @@ __global__ void __launch_bounds__(TY, sizeof(T) == 8 ? FDLBM_FUSED_MINB64 : FDLB
     auto slot = [](int c) { return (NS & (NS - 1)) == 0 ? (c & (NS - 1)) : ((c % NS) + NS) % NS; };
     auto in_domain = [&](int c) { return P.x_periodic || (P.gx0 + c >= 0 && P.gx0 + c < P.W); };
 
+    // Interior strips (no y wrap inside the apron) fill their g stages with BULK asynchronous copies: one thread
+    // issues 9 cp.async.bulk of a whole stage row each (1056 bytes), completion is counted in bytes on the stage's
+    // mbarrier.  Strips that touch the wrap use per-thread 16-byte cp.async (stage_fill).
+    constexpr unsigned ROW_BYTES = (unsigned)(PT * sizeof(T));
+    const bool bulk = FDLBM_BULK_COPY && !STAGE_F && y0 - HALO >= 0 && y0 + TY + HALO <= H;  // CTA-uniform
+    if (t == 0) {
+#pragma unroll
+        for (int s_ = 0; s_ < NS; ++s_) mbar_init(&bars[s_], 1);
+        mbar_fence_init();
+    }
+    __syncthreads();
+
     // one pipeline step: g column v+2+D (and f column v+1+D when staged); only columns this run reads
     auto prefetch = [&](int v) {
         const int cg = v + 2 + D, cf = v + 1 + D;
-        if (cg >= xs - 2 && cg <= xe + 1)
-            stage_fill<T, TY, PT, HALO>(gst + slot(cg) * FAM, P.src + lat_idx(Hp, cg, 9, 0), Hp, H, y0, ny);
+        if (cg >= xs - 2 && cg <= xe + 1) {
+            T *stage = gst + slot(cg) * FAM;
+            const T *col = P.src + lat_idx(Hp, cg, 9, 0);
+            if (bulk) {
+                if (t == 0) {
+                    mbar_expect_tx(&bars[slot(cg)], 9u * ROW_BYTES);
+#pragma unroll
+                    for (int pop = 0; pop < 9; ++pop)
+                        bulk_g2s(stage + pop * PT, col + (size_t)pop * Hp + (y0 - HALO), ROW_BYTES, &bars[slot(cg)]);
+                }
+            } else {
+                stage_fill<T, TY, PT, HALO>(stage, col, Hp, H, y0, ny);
+            }
+        }
         if (STAGE_F && cf >= xs - 1 && cf <= xe)
             stage_fill<T, TY, PT, HALO>(fst + slot(cf) * FAM, P.src + lat_idx(Hp, cf, 0, 0), Hp, H, y0, ny);
         cp_async_commit();
+    };
+    // wait until g column c has landed in its stage (bulk path: the fill of column c is the
+    // ((c - (xs-2)) / NS)-th use of its mbarrier, whose parity is waited for)
+    auto landed = [&](int c) {
+        if (bulk) mbar_wait(&bars[slot(c)], (unsigned)(((c - (xs - 2)) / NS) & 1));
     };
     // Per-cell flags are plain global loads issued two columns ahead of their use and carried RAW in
     // registers: nothing depends on them until they are decoded two iterations later, so their latency
@@ -244,17 +309,22 @@ __global__ void __launch_bounds__(TY, sizeof(T) == 8 ? FDLBM_FUSED_MINB64 : FDLB
         eq1 = load_flags(xs + 2, ye1);
     }
     cp_async_wait<D>();  // g columns <= xs have landed (this thread's share)
+    landed(xs - 2);
+    landed(xs - 1);
+    landed(xs);
     __syncthreads();
     psi_column(xs - 1, decode(rf_m1, y), decode(re_m1, ye1), g_nxt, pm_m, pm_0, pm_p);
     __syncthreads();
     prefetch(xs - 1);
     cp_async_wait<D>();  // g column xs+1 has landed
+    landed(xs + 1);
     __syncthreads();
     fl_cur = decode(rf_0, y);
     psi_column(xs, fl_cur, decode(re_0, ye1), g_cur, p0_m, p0_0, p0_p);
 
     for (int x = xs; x < xe; ++x) {
         cp_async_wait<D - 1>();  // g column x+2 (and staged f column x+1) have landed
+        landed(x + 2);
         __syncthreads();         // ... for every thread; and everybody is done with iteration x-1
         // Decode the flags of column x+1 BEFORE any new global load is issued: they were loaded two iterations
         // ago, but the hardware scoreboard slots are shared -- decoding them after this iteration's f loads

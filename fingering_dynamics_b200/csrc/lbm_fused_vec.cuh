@@ -16,6 +16,9 @@
 #ifndef FDLBM_F32_VEC
 #define FDLBM_F32_VEC 2
 #endif
+#ifndef FDLBM_BULK_COPY_VEC
+#define FDLBM_BULK_COPY_VEC 0
+#endif
 
 namespace fdlbm {
 
@@ -39,6 +42,7 @@ __global__ void __launch_bounds__(NT, sizeof(T) == 8 ? FDLBM_FUSED_MINB64 : FDLB
     static_assert((NS & (NS - 1)) == 0, "stage ring must be a power of two");
     extern __shared__ __align__(16) unsigned char smem_raw[];
     T *gst = reinterpret_cast<T *>(smem_raw);  // [NS][9][PT]
+    __shared__ __align__(8) unsigned long long bars[NS];  // one mbarrier per g stage (bulk-copy path)
     const int t = threadIdx.x, lane = t & 31;
     const int H = P.H, Hp = P.Hp;
 
@@ -65,12 +69,38 @@ __global__ void __launch_bounds__(NT, sizeof(T) == 8 ? FDLBM_FUSED_MINB64 : FDLB
     auto slot = [](int c) { return c & (NS - 1); };
     auto in_domain = [&](int c) { return P.x_periodic || (P.gx0 + c >= 0 && P.gx0 + c < P.W); };
 
+    // interior strips: bulk asynchronous copies completing on the stage's mbarrier (see k_fused)
+    constexpr unsigned ROW_BYTES = (unsigned)(PT * sizeof(T));
+    // (measured for fp32 / two rows per thread: 26.7 GLUPS with bulk copies vs 30.2 with per-thread cp.async: off)
+    const bool bulk = FDLBM_BULK_COPY_VEC && y0 - HALO >= 0 && y0 + ROWS + HALO <= H;  // CTA-uniform
+    if (t == 0) {
+#pragma unroll
+        for (int s_ = 0; s_ < NS; ++s_) mbar_init(&bars[s_], 1);
+        mbar_fence_init();
+    }
+    __syncthreads();
+
     // one pipeline step: g column v+2+D, rows [y0-HALO, y0+ny+HALO) with the y wrap applied
     auto prefetch = [&](int v) {
         const int cg = v + 2 + D;
-        if (cg >= xs - 2 && cg <= xe + 1)
-            stage_fill<T, NT, PT, HALO>(gst + slot(cg) * FAM, P.src + lat_idx(Hp, cg, 9, 0), Hp, H, y0, ny);
+        if (cg >= xs - 2 && cg <= xe + 1) {
+            T *stage = gst + slot(cg) * FAM;
+            const T *col = P.src + lat_idx(Hp, cg, 9, 0);
+            if (bulk) {
+                if (t == 0) {
+                    mbar_expect_tx(&bars[slot(cg)], 9u * ROW_BYTES);
+#pragma unroll
+                    for (int pop = 0; pop < 9; ++pop)
+                        bulk_g2s(stage + pop * PT, col + (size_t)pop * Hp + (y0 - HALO), ROW_BYTES, &bars[slot(cg)]);
+                }
+            } else {
+                stage_fill<T, NT, PT, HALO>(stage, col, Hp, H, y0, ny);
+            }
+        }
         cp_async_commit();
+    };
+    auto landed = [&](int c) {
+        if (bulk) mbar_wait(&bars[slot(c)], (unsigned)(((c - (xs - 2)) / NS) & 1));
     };
     // raw flags of the thread's rows (reflect bytes packed little-endian, solid-mask word) and of one edge row
     auto load_flags = [&](int c, int yy, int n) -> RawFlags {
@@ -143,6 +173,9 @@ __global__ void __launch_bounds__(NT, sizeof(T) == 8 ? FDLBM_FUSED_MINB64 : FDLB
         hq1 = load_flags(xs + 2, ye_hi, 1);
     }
     cp_async_wait<D>();
+    landed(xs - 2);
+    landed(xs - 1);
+    landed(xs);
     __syncthreads();
 #pragma unroll
     for (int v = 0; v < VEC; ++v) fl_nxt[v] = decode(rf_m1, yb, v);
@@ -150,6 +183,7 @@ __global__ void __launch_bounds__(NT, sizeof(T) == 8 ? FDLBM_FUSED_MINB64 : FDLB
     __syncthreads();
     prefetch(xs - 1);
     cp_async_wait<D>();
+    landed(xs + 1);
     __syncthreads();
 #pragma unroll
     for (int v = 0; v < VEC; ++v) fl_cur[v] = decode(rf_0, yb, v);
@@ -157,6 +191,7 @@ __global__ void __launch_bounds__(NT, sizeof(T) == 8 ? FDLBM_FUSED_MINB64 : FDLB
 
     for (int x = xs; x < xe; ++x) {
         cp_async_wait<D - 1>();  // g column x+2 has landed
+        landed(x + 2);
         __syncthreads();         // ... for every thread; and everybody is done with iteration x-1
         // decode the flags of column x+1 before any new global load is issued (see k_fused)
         unsigned fl_lo_n = decode(lq0, ye_lo, 0), fl_hi_n = decode(hq0, ye_hi, 0);
