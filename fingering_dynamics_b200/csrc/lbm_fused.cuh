@@ -8,8 +8,8 @@
 //   * the g columns are streamed from HBM into a shared-memory stage ring with cp.async (16-byte
 //     chunks, D columns ahead of the compute front): the loads of the next columns are in flight while
 //     the current column is collided, and the strip's neighbours in y are reachable for the psi halo;
-//   * the f columns are either staged the same way (STAGE_F) or pulled straight into registers at the
-//     top of the iteration from lines that were prefetched into L2 a few columns ahead;
+//   * the f columns are pulled straight into registers at the top of the iteration from lines that were
+//     prefetched into L2 two columns ahead (staging f too halves the resident CTAs and measured slower);
 //   * iteration x:  wait for g column x+2 (the only barrier) -> pull g of column x+1 from the stages
 //     (+ bounce-back, Zou-He) -> psi_new(x+1, y); rows y-1 / y+1 arrive by WARP SHUFFLE from the
 //     neighbouring lanes (the two end lanes of a warp evaluate their outer neighbour themselves), the
@@ -38,15 +38,11 @@ namespace fdlbm {
 #ifndef FDLBM_FUSED_MINB32
 #define FDLBM_FUSED_MINB32 4
 #endif
-#ifndef FDLBM_STAGE_F
-#define FDLBM_STAGE_F 0
-#endif
 #ifndef FDLBM_BULK_COPY
 #define FDLBM_BULK_COPY 1  // g stages of interior strips through cp.async.bulk + mbarrier (0: per-thread cp.async only)
 #endif
 constexpr int FUSED_TY = FDLBM_FUSED_TY;  // rows per strip = threads per CTA
 constexpr int FUSED_D = FDLBM_FUSED_D;    // cp.async prefetch distance in columns
-constexpr bool FUSED_STAGE_F = FDLBM_STAGE_F != 0;
 #ifndef FDLBM_L2_AHEAD
 #define FDLBM_L2_AHEAD 2
 #endif
@@ -102,13 +98,13 @@ __device__ __forceinline__ void mbar_wait(void *bar, unsigned parity)
         : "memory");
 }
 
-template <typename T, int TY, bool STAGE_F>
+template <typename T, int TY>
 struct FusedCfg {
     static constexpr int HALO = 16 / (int)sizeof(T);      // rows of apron per side: keeps 16-byte chunks aligned
     static constexpr int PT = TY + 2 * HALO;              // stage row pitch (elements)
-    static constexpr int NS = 3 + FUSED_D;                // stages per ring (g: x..x+2+D, f: x-1..x+1+D)
+    static constexpr int NS = 3 + FUSED_D;                // stages of the g ring (columns x..x+2+D)
     static constexpr int FAM = 9 * PT;                    // elements of one stage (one family of one column)
-    static constexpr size_t SMEM = (size_t)((STAGE_F ? 2 : 1) * NS * FAM) * sizeof(T);
+    static constexpr size_t SMEM = (size_t)(NS * FAM) * sizeof(T);
 };
 
 // Fill one stage: 9 populations of one family of the column whose record starts at `col` (pop 0 of the
@@ -172,15 +168,14 @@ struct RawFlags {
 
 // HPC > 0: the row pitch Hp is the compile-time constant HPC (all population offsets become immediates of the
 // loads / stores / cp.async); HPC == 0: Hp is read from the parameters (any grid height).
-template <typename T, int TY, bool STAGE_F, int HPC>
+template <typename T, int TY, int HPC>
 __global__ void __launch_bounds__(TY, sizeof(T) == 8 ? FDLBM_FUSED_MINB64 : FDLBM_FUSED_MINB32) k_fused(const __grid_constant__ LbmParams<T> P, int nyt, int chunk)
 {
-    using C = FusedCfg<T, TY, STAGE_F>;
+    using C = FusedCfg<T, TY>;
     constexpr int D = FUSED_D, NS = C::NS, PT = C::PT, HALO = C::HALO, FAM = C::FAM;
     constexpr unsigned FULL = 0xffffffffu;
     extern __shared__ __align__(16) unsigned char smem_raw[];
     T *gst = reinterpret_cast<T *>(smem_raw);        // [NS][9][PT]
-    T *fst = gst + NS * FAM;                         // [NS][9][PT] when STAGE_F
     __shared__ __align__(8) unsigned long long bars[NS];  // one mbarrier per g stage (bulk-copy path)
     const int t = threadIdx.x, lane = t & 31;
     const int H = P.H, Hp = HPC > 0 ? HPC : P.Hp;
@@ -214,7 +209,7 @@ __global__ void __launch_bounds__(TY, sizeof(T) == 8 ? FDLBM_FUSED_MINB64 : FDLB
     // issues 9 cp.async.bulk of a whole stage row each (1056 bytes), completion is counted in bytes on the stage's
     // mbarrier.  Strips that touch the wrap use per-thread 16-byte cp.async (stage_fill).
     constexpr unsigned ROW_BYTES = (unsigned)(PT * sizeof(T));
-    const bool bulk = FDLBM_BULK_COPY && !STAGE_F && y0 - HALO >= 0 && y0 + TY + HALO <= H;  // CTA-uniform
+    const bool bulk = FDLBM_BULK_COPY && y0 - HALO >= 0 && y0 + TY + HALO <= H;  // CTA-uniform
     if (t == 0) {
 #pragma unroll
         for (int s_ = 0; s_ < NS; ++s_) mbar_init(&bars[s_], 1);
@@ -222,9 +217,9 @@ __global__ void __launch_bounds__(TY, sizeof(T) == 8 ? FDLBM_FUSED_MINB64 : FDLB
     }
     __syncthreads();
 
-    // one pipeline step: g column v+2+D (and f column v+1+D when staged); only columns this run reads
+    // one pipeline step: g column v+2+D; only columns this run reads
     auto prefetch = [&](int v) {
-        const int cg = v + 2 + D, cf = v + 1 + D;
+        const int cg = v + 2 + D;
         if (cg >= xs - 2 && cg <= xe + 1) {
             T *stage = gst + slot(cg) * FAM;
             const T *col = P.src + lat_idx(Hp, cg, 9, 0);
@@ -239,8 +234,6 @@ __global__ void __launch_bounds__(TY, sizeof(T) == 8 ? FDLBM_FUSED_MINB64 : FDLB
                 stage_fill<T, TY, PT, HALO>(stage, col, Hp, H, y0, ny);
             }
         }
-        if (STAGE_F && cf >= xs - 1 && cf <= xe)
-            stage_fill<T, TY, PT, HALO>(fst + slot(cf) * FAM, P.src + lat_idx(Hp, cf, 0, 0), Hp, H, y0, ny);
         cp_async_commit();
     };
     // wait until g column c has landed in its stage (bulk path: the fill of column c is the
@@ -323,7 +316,7 @@ __global__ void __launch_bounds__(TY, sizeof(T) == 8 ? FDLBM_FUSED_MINB64 : FDLB
     psi_column(xs, fl_cur, decode(re_0, ye1), g_cur, p0_m, p0_0, p0_p);
 
     for (int x = xs; x < xe; ++x) {
-        cp_async_wait<D - 1>();  // g column x+2 (and staged f column x+1) have landed
+        cp_async_wait<D - 1>();  // g column x+2 has landed
         landed(x + 2);
         __syncthreads();         // ... for every thread; and everybody is done with iteration x-1
         // Decode the flags of column x+1 BEFORE any new global load is issued: they were loaded two iterations
@@ -332,9 +325,9 @@ __global__ void __launch_bounds__(TY, sizeof(T) == 8 ? FDLBM_FUSED_MINB64 : FDLB
         fl_nxt = decode(fq0, y);
         unsigned fe_nxt = decode(eq0, ye1);
         asm volatile("" : "+r"(fl_nxt), "+r"(fe_nxt)::"memory");
-        prefetch(x);             // overwrites the stage of g column x-1 (f column x-2): no longer read
+        prefetch(x);             // overwrites the stage of g column x-1: no longer read
         T f[9];
-        if (!STAGE_F) {
+        {
             // f of column x straight into registers; consumed after the psi phase below
             if (active) pull_hp(P, Hp, x, y, 0, fl_cur & 0xffu, f);
             // and the lines of f column x+L2_AHEAD into L2: one prefetch per 128-byte line of the strip
@@ -351,8 +344,6 @@ __global__ void __launch_bounds__(TY, sizeof(T) == 8 ? FDLBM_FUSED_MINB64 : FDLB
         const RawFlags eq2 = edge ? load_flags(x + 3, ye1) : z;
         psi_column(x + 1, fl_nxt, fe_nxt, g_nxt, pp_m, pp_0, pp_p);
         if (active) {
-            if (STAGE_F)
-                pull_staged<T, PT>(fst + slot(x - 1) * FAM, fst + slot(x) * FAM, fst + slot(x + 1) * FAM, j, fl_cur & 0xffu, f);
             if (P.zou_he) {
                 const int gx_ = P.gx0 + x;
                 if (gx_ == 0 || gx_ == P.W - 1) zou_he_f(P, x, gx_, y, f, PullRow<T>());
@@ -407,8 +398,8 @@ inline int fused_chunk(int nyt, int n_cta, int Wl)
 template <typename T, int HPC>
 int launch_fused_hp(const LbmParams<T> &P, cudaStream_t stream)
 {
-    using C = FusedCfg<T, FUSED_TY, FUSED_STAGE_F>;
-    auto kern = k_fused<T, FUSED_TY, FUSED_STAGE_F, HPC>;
+    using C = FusedCfg<T, FUSED_TY>;
+    auto kern = k_fused<T, FUSED_TY, HPC>;
     static int n_cta = 0;  // per instantiation; device properties do not change within a process
     if (n_cta == 0) {
         int dev = 0, sms = 0, occ = 0;
