@@ -270,6 +270,14 @@ def wall_rows(f_behind, g_behind, f, g):
     _ops.bounce_back(geo.reflect_bits_wall_rows(H, W, 0, H - 1), f_behind, g_behind, f, g)
 
 
+def save_frames(frames, path):
+    """Write psi frames in the format the reference's openmovie.py reads (openmovie.py:14-15): a pickled sequence
+    `cc` with cc[i] a (H, W) array.  fingering.py accumulates the same thing in RAM (fingering.py:557,565-566)."""
+    import pickle
+    with open(path, "wb") as fh:
+        pickle.dump(np.asarray(frames), fh)
+
+
 def run_loop(cm, reflect, n_steps, frames_every=0, dtype="f64"):
     """Advance `cm` n_steps reference iterations on the GPU; returns the list of psi frames taken every
     `frames_every` steps BEFORE the step, like fingering.py:565-566 (empty if 0)."""

@@ -156,3 +156,14 @@ def test_contact_angle_estimator_on_analytic_caps():
         psi = np.tanh((R - np.sqrt((xx - 100.3) ** 2 + (yy - yc) ** 2)) / 1.5)
         assert abs(pp.droplet_contact_angle(psi) - th) < 0.5
     assert pp.interface_shift(psi, np.roll(psi, 1, axis=1)) == pytest.approx(1.0, abs=1e-6)
+
+
+def test_frame_file_format_matches_openmovie(tmp_path):
+    """openmovie.py:14-15 unpickles `cc` and indexes cc[i] as an (H, W) array"""
+    import pickle
+    from fingering_dynamics_b200.lattice_boltzmann._compute import save_frames
+    frames = [np.full((4, 5), float(k)) for k in range(3)]
+    p = tmp_path / "f_list_test.txt"
+    save_frames(frames, p)
+    cc = pickle.load(open(p, "rb"))
+    assert len(cc) == 3 and cc[1].shape == (4, 5) and cc[2][0, 0] == 2.0
