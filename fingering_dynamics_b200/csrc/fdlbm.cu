@@ -208,7 +208,8 @@ int ensure_fields(fdlbm_engine *e)
     return 0;
 }
 
-dim3 cell_grid(const fdlbm_engine *e, int ncol) { return dim3((e->cfg.H + TPB - 1) / TPB, ncol); }
+// 1-D grid of (y tile, column) CTAs, y tiles fastest (decoded by block_cell)
+dim3 cell_grid(const fdlbm_engine *e, int ncol) { return dim3((unsigned)((e->cfg.H + TPB - 1) / TPB) * (unsigned)ncol); }
 
 // local periodic wrap of the two ghost columns per side (single slab spanning the whole x range)
 int wrap_ghosts(fdlbm_engine *e, void *lat)

@@ -6,14 +6,24 @@ namespace fdlbm {
 
 constexpr int TPB = 128;  // threads per block along y (the contiguous axis)
 
+// One CTA per (y tile, column); the launch grid is 1-D (y tiles fastest) so that the column count is not bound by
+// the 65535 limit of gridDim.y.  Returns the cell of this thread: row y (may be >= H), column index col.
+__device__ __forceinline__ void block_cell(int H, int &y, int &col)
+{
+    const unsigned nyt = (unsigned)(H + TPB - 1) / TPB;
+    y = (int)(blockIdx.x % nyt) * TPB + threadIdx.x;
+    col = (int)(blockIdx.x / nyt);
+}
+
 // ---------------------------------------------------------------------------------------------
 // two-pass path, pass 1: psi_new for columns [xl_begin, xl_begin + gridDim.y)
 // ---------------------------------------------------------------------------------------------
 template <typename T>
 __global__ void __launch_bounds__(TPB) k_psi(const __grid_constant__ LbmParams<T> P, int xl_begin)
 {
-    const int y = blockIdx.x * TPB + threadIdx.x;
-    const int xl = xl_begin + blockIdx.y;
+    int y, xl;
+    block_cell(P.H, y, xl);
+    xl += xl_begin;
     if (y >= P.H) return;
     T g[9];
     const unsigned bits = P.reflect[cell_idx(P.Hp, xl, y)];
@@ -29,8 +39,8 @@ __global__ void __launch_bounds__(TPB) k_psi(const __grid_constant__ LbmParams<T
 template <typename T, bool FINALIZE>
 __global__ void __launch_bounds__(TPB) k_step_twopass(const __grid_constant__ LbmParams<T> P, FieldPtrs<T> out)
 {
-    const int y = blockIdx.x * TPB + threadIdx.x;
-    const int xl = blockIdx.y;
+    int y, xl;
+    block_cell(P.H, y, xl);
     if (y >= P.H) return;
     const size_t c = cell_idx(P.Hp, xl, y);
     const unsigned bits = P.reflect[c];
@@ -76,8 +86,8 @@ template <typename T>
 __global__ void __launch_bounds__(TPB) k_collide_first(const __grid_constant__ LbmParams<T> P, FieldPtrs<T> in,
                                                        const T *psi)
 {
-    const int y = blockIdx.x * TPB + threadIdx.x;
-    const int xl = blockIdx.y;
+    int y, xl;
+    block_cell(P.H, y, xl);
     if (y >= P.H) return;
     if (is_solid(P, xl, y)) return;
     const size_t c = cell_idx(P.Hp, xl, y);
@@ -155,7 +165,8 @@ __global__ void k_transpose_out(const TS *__restrict__ base, size_t xstride, int
 template <typename T>
 __global__ void __launch_bounds__(TPB) k_count_nonfinite(const T *__restrict__ lat, int H, int Hp, unsigned long long *n_bad)
 {
-    const int y = blockIdx.x * TPB + threadIdx.x, xl = blockIdx.y;
+    int y, xl;
+    block_cell(H, y, xl);
     unsigned bad = 0;
     if (y < H) {
         const T *s = lat + lat_idx(Hp, xl, 0, y);

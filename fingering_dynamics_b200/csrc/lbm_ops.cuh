@@ -10,7 +10,8 @@ namespace fdlbm {
 template <typename T>
 __global__ void __launch_bounds__(TPB) k_op_stream(const __grid_constant__ LbmParams<T> P)
 {
-    const int y = blockIdx.x * TPB + threadIdx.x, xl = blockIdx.y;
+    int y, xl;
+    block_cell(P.H, y, xl);
     if (y >= P.H) return;
     T f[9], g[9];
     pull(P, xl, y, 0, 0u, f);
@@ -22,7 +23,8 @@ __global__ void __launch_bounds__(TPB) k_op_stream(const __grid_constant__ LbmPa
 template <typename T>
 __global__ void __launch_bounds__(TPB) k_op_bounce_back(const __grid_constant__ LbmParams<T> P)
 {
-    const int y = blockIdx.x * TPB + threadIdx.x, xl = blockIdx.y;
+    int y, xl;
+    block_cell(P.H, y, xl);
     if (y >= P.H) return;
     const unsigned bits = P.reflect[cell_idx(P.Hp, xl, y)];
     if (!bits) return;
@@ -39,7 +41,8 @@ __global__ void __launch_bounds__(TPB) k_op_bounce_back(const __grid_constant__ 
 template <typename T>
 __global__ void __launch_bounds__(TPB) k_op_stencils(const __grid_constant__ LbmParams<T> P, FieldPtrs<T> out)
 {
-    const int y = blockIdx.x * TPB + threadIdx.x, xl = blockIdx.y;
+    int y, xl;
+    block_cell(P.H, y, xl);
     if (y >= P.H) return;
     const size_t c = cell_idx(P.Hp, xl, y);
     stencil_from_array(P, P.psi_old, xl, y, out.gx[c], out.gy[c], out.lap[c]);
@@ -65,8 +68,9 @@ struct LocalRow {
 template <typename T>
 __global__ void __launch_bounds__(TPB) k_op_zou_he(const __grid_constant__ LbmParams<T> P)
 {
-    const int y = blockIdx.x * TPB + threadIdx.x;
-    const int xl = blockIdx.y == 0 ? 0 : P.Wl - 1;
+    int y, face;
+    block_cell(P.H, y, face);
+    const int xl = face == 0 ? 0 : P.Wl - 1;
     if (y >= P.H) return;
     const int gx = P.gx0 + xl;
     T f[9], g[9];
@@ -87,7 +91,8 @@ __global__ void __launch_bounds__(TPB) k_op_zou_he(const __grid_constant__ LbmPa
 template <typename T>
 __global__ void __launch_bounds__(TPB) k_op_psi_local(const __grid_constant__ LbmParams<T> P)
 {
-    const int y = blockIdx.x * TPB + threadIdx.x, xl = blockIdx.y;
+    int y, xl;
+    block_cell(P.H, y, xl);
     if (y >= P.H) return;
     T s = P.psi_wall;
     if (!is_solid(P, xl, y)) {
@@ -102,7 +107,8 @@ __global__ void __launch_bounds__(TPB) k_op_psi_local(const __grid_constant__ Lb
 template <typename T>
 __global__ void __launch_bounds__(TPB) k_op_moments_local(const __grid_constant__ LbmParams<T> P, FieldPtrs<T> out)
 {
-    const int y = blockIdx.x * TPB + threadIdx.x, xl = blockIdx.y;
+    int y, xl;
+    block_cell(P.H, y, xl);
     if (y >= P.H) return;
     const size_t c = cell_idx(P.Hp, xl, y);
     T gx, gy, lap;
@@ -135,7 +141,8 @@ template <typename T>
 __global__ void __launch_bounds__(TPB) k_op_terms(const __grid_constant__ LbmParams<T> P, FieldPtrs<T> in, const T *psi,
                                                   T *eq_lat, T *force_lat)
 {
-    const int y = blockIdx.x * TPB + threadIdx.x, xl = blockIdx.y;
+    int y, xl;
+    block_cell(P.H, y, xl);
     if (y >= P.H) return;
     if (is_solid(P, xl, y)) return;
     const size_t c = cell_idx(P.Hp, xl, y);
@@ -167,7 +174,8 @@ template <typename T>
 __global__ void __launch_bounds__(TPB) k_op_algebra(const __grid_constant__ LbmParams<T> P, const T *psi_, const T *rho_,
                                                     const T *mu_, const T *p_, const T *lap_, FieldPtrs<T> out)
 {
-    const int y = blockIdx.x * TPB + threadIdx.x, xl = blockIdx.y;
+    int y, xl;
+    block_cell(P.H, y, xl);
     if (y >= P.H) return;
     const size_t c = cell_idx(P.Hp, xl, y);
     const T psi = psi_[c], rho = rho_[c], mu = mu_[c], p = p_[c], lap = lap_[c];
