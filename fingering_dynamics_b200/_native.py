@@ -12,7 +12,7 @@ import numpy as np
 _HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(_HERE, "csrc")
 LIB_PATH = os.path.join(CSRC, "libfdlbm.so")
-SOURCES = ["fdlbm.cu", "lbm_device.cuh", "lbm_kernels.cuh", "lbm_fused.cuh", "lbm_fused_vec.cuh", "lbm_ops.cuh"]
+SOURCES = ["fdlbm.cu", "lbm_device.cuh", "lbm_kernels.cuh", "lbm_fused.cuh", "lbm_fused_vec.cuh", "lbm_fused_f32.cuh", "lbm_ops.cuh"]
 HEADER = os.path.join(os.path.dirname(_HERE), "include", "fdlbm.h")
 
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17", "--shared",

@@ -511,12 +511,13 @@ int fdlbm_create(const fdlbm_config *cfg, fdlbm_engine **out)
     }
     CUE(cudaMalloc((void **)&e->flags, 256));
     CUE(cudaMemsetAsync(e->flags, 0, 256, e->stream));
-    CUE(cudaMalloc(&e->reflect, e->plane_elems()));
-    CUE(cudaMemsetAsync(e->reflect, 0, e->plane_elems(), e->stream));
+    // the flag arrays carry one spare (zero) column: the step kernels load flags three columns ahead without a bound check
+    CUE(cudaMalloc(&e->reflect, e->plane_elems() + e->Hp));
+    CUE(cudaMemsetAsync(e->reflect, 0, e->plane_elems() + e->Hp, e->stream));
     CUE(cudaMalloc(&e->solid_bytes, e->plane_elems()));
     CUE(cudaMemsetAsync(e->solid_bytes, 0, e->plane_elems(), e->stream));
-    CUE(cudaMalloc(&e->solid, e->plane_elems() / 8));
-    CUE(cudaMemsetAsync(e->solid, 0, e->plane_elems() / 8, e->stream));
+    CUE(cudaMalloc(&e->solid, (e->plane_elems() + e->Hp) / 8));
+    CUE(cudaMemsetAsync(e->solid, 0, (e->plane_elems() + e->Hp) / 8, e->stream));
 #undef CUE
     if (cfg->zou_he != FDLBM_ZH_NONE) {
         int rc = upload_profile(e, cfg->inlet_ux, &e->inlet);

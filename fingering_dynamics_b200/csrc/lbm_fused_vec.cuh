@@ -8,6 +8,9 @@
 #pragma once
 #include <type_traits>
 
+#include <cstdlib>
+#include <cstring>
+
 #include "lbm_fused.cuh"
 
 #ifndef FDLBM_FUSED_MINB32V
@@ -32,9 +35,9 @@ struct VecCfg {
     static constexpr size_t SMEM = (size_t)(NS * FAM) * sizeof(T);
 };
 
+// columns [xs, xe) of strip yt (the body of k_fused_vec; also run by the face CTAs of k_fused_f32p)
 template <typename T, int NT, int VEC>
-__global__ void __launch_bounds__(NT, sizeof(T) == 8 ? FDLBM_FUSED_MINB64 : FDLBM_FUSED_MINB32V)
-    k_fused_vec(const __grid_constant__ LbmParams<T> P, int nyt, int chunk)
+__device__ __forceinline__ void fused_vec_strip(const LbmParams<T> &P, const int yt, const int xs, const int xe)
 {
     using C = VecCfg<T, NT, VEC>;
     constexpr int D = FUSED_D, NS = C::NS, PT = C::PT, HALO = C::HALO, FAM = C::FAM, ROWS = C::ROWS;
@@ -46,9 +49,6 @@ __global__ void __launch_bounds__(NT, sizeof(T) == 8 ? FDLBM_FUSED_MINB64 : FDLB
     const int t = threadIdx.x, lane = t & 31;
     const int H = P.H, Hp = P.Hp;
 
-    const int yt = blockIdx.x % nyt;
-    const int xs = (blockIdx.x / nyt) * chunk;
-    const int xe = min(P.Wl, xs + chunk);
     const int y0 = yt * ROWS;
     const int yb = y0 + VEC * t;                 // first row of this thread
     const int ny = min(ROWS, H - y0);            // rows of this strip
@@ -283,6 +283,14 @@ __global__ void __launch_bounds__(NT, sizeof(T) == 8 ? FDLBM_FUSED_MINB64 : FDLB
 }
 
 template <typename T, int NT, int VEC>
+__global__ void __launch_bounds__(NT, sizeof(T) == 8 ? FDLBM_FUSED_MINB64 : FDLBM_FUSED_MINB32V)
+    k_fused_vec(const __grid_constant__ LbmParams<T> P, int nyt, int chunk)
+{
+    const int xs = (blockIdx.x / nyt) * chunk;
+    fused_vec_strip<T, NT, VEC>(P, blockIdx.x % nyt, xs, min(P.Wl, xs + chunk));
+}
+
+template <typename T, int NT, int VEC>
 int launch_fused_vec(const LbmParams<T> &P, cudaStream_t stream)
 {
     using C = VecCfg<T, NT, VEC>;
@@ -308,6 +316,12 @@ int launch_fused_vec(const LbmParams<T> &P, cudaStream_t stream)
     return 0;
 }
 
+}  // namespace fdlbm
+
+#include "lbm_fused_f32.cuh"
+
+namespace fdlbm {
+
 // the step kernel used for each storage type
 template <typename T>
 int launch_fused_auto(const LbmParams<T> &P, cudaStream_t stream);
@@ -324,6 +338,12 @@ template <>
 inline int launch_fused_auto<float>(const LbmParams<float> &P, cudaStream_t stream)
 {
 #if FDLBM_F32_VEC == 2
+    // even heights: packed two-row kernel (lbm_fused_f32.cuh); FDLBM_F32_KERNEL=vec selects the scalar two-row kernel
+    static const bool force_vec = [] {
+        const char *v = getenv("FDLBM_F32_KERNEL");
+        return v && strcmp(v, "vec") == 0;
+    }();
+    if (P.H % 2 == 0 && !force_vec && f32p::applicable(P)) return f32p::launch(P, stream);
     return launch_fused_vec<float, FUSED_TY, 2>(P, stream);
 #else
     return launch_fused<float>(P, stream);

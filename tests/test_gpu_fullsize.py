@@ -94,6 +94,18 @@ def test_fused_equals_twopass_on_random_geometry_and_odd_sizes(variant, H, W):
     """odd H / W (strip tails, partial warps, one-row threads of the two-rows-per-thread fp32 kernel), random
     solid flags and random reflect bits: the fused kernels must reproduce the two-pass kernel --
     bit for bit in fp64, to fp32 rounding in fp32."""
+    _fused_vs_twopass(variant, H, W)
+
+
+@pytest.mark.parametrize("variant", ["fp", "fg", "va"])
+@pytest.mark.parametrize("H,W", [(4, 33), (66, 40), (130, 96), (194, 20), (256, 64), (258, 50), (512, 37), (2048, 24)])
+def test_fused_equals_twopass_on_random_geometry_and_even_sizes(variant, H, W):
+    """even H: the fp32 engine runs the packed two-row kernel (lbm_fused_f32.cuh) -- one-lane warps at the strip tail
+    (H = 66, 130, 194), strips with a wrapping apron, a second strip (258, 512), the compile-time row pitch (2048)"""
+    _fused_vs_twopass(variant, H, W)
+
+
+def _fused_vs_twopass(variant, H, W):
     from fingering_dynamics_b200 import Engine
     rng = np.random.default_rng(H * 1000 + W)
     solid = (rng.random((H, W)) < 0.12).astype(np.uint8)
@@ -107,7 +119,11 @@ def test_fused_equals_twopass_on_random_geometry_and_odd_sizes(variant, H, W):
     else:
         kw.update(zou_he="none", x_periodic=True, psi_y_wall=True)
     fluid = solid == 0
-    psi = np.where(fluid, np.tanh(rng.standard_normal((H, W))), kw["psi_wall"])
+    # a smooth order parameter plus a little noise: white noise in psi means O(1) chemical-potential forces, single
+    # cells then blow up within 3 steps and an fp32 comparison would only measure those cells
+    yy, xx = np.mgrid[:H, :W]
+    smooth = np.sin(2 * np.pi * xx / 23.0 + 0.3) * np.cos(2 * np.pi * yy / 17.0) + 0.3 * np.sin(2 * np.pi * (xx + yy) / 9.0)
+    psi = np.where(fluid, 0.7 * smooth + 0.02 * np.tanh(rng.standard_normal((H, W))), kw["psi_wall"])
     rho = 1.0 + 0.01 * rng.standard_normal((H, W))
     w = np.array([4 / 9] + [1 / 9] * 4 + [1 / 36] * 4)[:, None, None]
     f = np.ascontiguousarray(w * rho * (1 + 0.01 * rng.standard_normal((9, H, W))) * fluid)
@@ -130,7 +146,8 @@ def test_fused_equals_twopass_on_random_geometry_and_odd_sizes(variant, H, W):
             if exact:
                 assert np.array_equal(a, b, equal_nan=True) and np.isfinite(a).all(), (dtype, k)
             else:
-                assert np.max(np.abs(a - b)) <= 2e-5 * max(1.0, np.max(np.abs(b))), (dtype, k)
+                # (the packed fp32 kernel evaluates the collision in its even / odd form: same algebra, other rounding)
+                assert np.max(np.abs(a - b)) <= 5e-5 * max(1.0, np.max(np.abs(b))), (dtype, k, np.max(np.abs(a - b)), np.max(np.abs(b)))
 
 
 def test_grid_wider_than_65535_columns_matches_the_oracle():
