@@ -20,6 +20,13 @@
 //   * columns next to the Zou-He faces / outside the domain take the generic scalar iteration (rare).
 //
 // Requires an even grid height (aligned row pairs); odd heights use k_fused_vec.
+//
+// Measured on B200 (8192x2048, same box, two interleaved repetitions; profiles/README.md): this kernel 37.9 GLUPS
+// (83 % of the HBM roofline; the access pattern itself copies at 93.5 % of memcpy speed, gpurun_in/micro/pattern.cu).
+// Variants that put MORE memory requests in flight were all slower: f loads issued one column ahead -1.6 %
+// (ptxas makes the loop head wait for every global load still in flight, so the stall only moves there); f one
+// column ahead in its own registers with g reloaded from a five-stage ring -4 %; L2 prefetch of f 4 columns ahead
+// -13 %, of g 4 columns ahead -9 %; eight g stages (2 CTAs/SM) -4 %.  Keep the loads late and the ring short.
 #pragma once
 #include "lbm_fused_vec.cuh"
 
@@ -76,16 +83,8 @@ FDLBM_DI float lds_f(const float *p)
     return v;
 }
 
-#ifndef FDLBM_F32_D
-#define FDLBM_F32_D 1      // cp.async distance of the g columns (columns ahead of the psi front)
-#endif
-#ifndef FDLBM_F32_L2G
-#define FDLBM_F32_L2G 0    // L2 prefetch of the g columns, this many columns ahead of their cp.async (0 = off)
-#endif
 struct Cfg {
-    static constexpr int D = FDLBM_F32_D, NS = D + 3 <= 4 ? 4 : 8;  // stage ring: columns x .. x+2+D, a power of two
-    static_assert(D >= 1 && D + 3 <= NS, "prefetch distance");
-    static constexpr int NT = 128, ROWS = 256, HALO = 4, PT = ROWS + 2 * HALO, FAM = 9 * PT;
+    static constexpr int NT = 128, ROWS = 256, HALO = 4, PT = ROWS + 2 * HALO, NS = 4, FAM = 9 * PT;
     static constexpr size_t SMEM = (size_t)NS * FAM * sizeof(float);
 };
 
@@ -188,9 +187,10 @@ __global__ void __launch_bounds__(Cfg::NT, 3)
     k_fused_f32p(const __grid_constant__ LbmParams<float> P, int nyt, int chunk, int fx0, int fx1, int n_fast)
 {
     typedef float T;
-    constexpr int D = Cfg::D, NS = Cfg::NS, PT = Cfg::PT, HALO = Cfg::HALO, FAM = Cfg::FAM, ROWS = Cfg::ROWS, NT = Cfg::NT;
+    constexpr int D = FUSED_D, NS = Cfg::NS, PT = Cfg::PT, HALO = Cfg::HALO, FAM = Cfg::FAM, ROWS = Cfg::ROWS, NT = Cfg::NT;
     constexpr unsigned FULL = 0xffffffffu;
-    static_assert(VecCfg<float, NT, 2>::SMEM <= Cfg::SMEM && VecCfg<float, NT, 2>::ROWS == ROWS, "same strips as k_fused_vec");
+    static_assert(D == 1 && NS == 4, "stage ring of four columns, one column ahead");
+    static_assert(VecCfg<float, NT, 2>::SMEM == Cfg::SMEM && VecCfg<float, NT, 2>::ROWS == ROWS, "same strips as k_fused_vec");
     if ((int)blockIdx.x >= n_fast) {  // face CTA
         const int k = (int)blockIdx.x - n_fast, side = k / nyt;
         const bool left = fx0 > 0 && side == 0;
@@ -342,14 +342,37 @@ __global__ void __launch_bounds__(Cfg::NT, 3)
         q_hi = edge_hi ? (edge_lo ? e2 : e) : up;
     };
 
-    p2 g_cur[9], f[9];
+    p2 g_cur[9];
     p2 pm, p0, pp;                                   // psi_new of the row pair on columns x-1, x, x+1
     T pm_lo, pm_hi, p0_lo, p0_hi, pp_lo, pp_hi;      // ... and of the rows below / above the pair
-    unsigned fl_cur[2], fl_nxt[2], fe_nxt;           // decoded flags: own pair of columns x, x+1; outer row of column x+1
+    unsigned fl_cur[2], fl_nxt[2];
     const RawFlags z{0u, 0u};
-    RawFlags rq = z, re = z;                         // raw flags of column x+2 (own pair / outer row), decoded one iteration on
+    RawFlags fq0 = z, fq1 = z, eq0 = z, eq1 = z;     // look-ahead queues (columns x+1, x+2): own pair / outer row
     const int yef = e_ghost ? 0 : ye;                // row 0 stands in for a ghost row (flags masked at decode)
     const unsigned e_mask = e_ghost ? 0u : 0x1ffu;
+
+    // ---- warm-up: g columns xs-2 .. xs+1, psi of columns xs-1 and xs ------------------------------------
+    for (int v = xs - 4 - D; v < xs - 1; ++v) prefetch(v);
+    {
+        const RawFlags rf_m1 = load_flags(xs - 1, yb, nv), re_m1 = edge ? load_flags(xs - 1, yef, 1) : z;
+        const RawFlags rf_0 = load_flags(xs, yb, nv), re_0 = edge ? load_flags(xs, yef, 1) : z;
+        fq0 = load_flags(xs + 1, yb, nv);
+        fq1 = load_flags(xs + 2, yb, nv);
+        if (edge) {
+            eq0 = load_flags(xs + 1, yef, 1);
+            eq1 = load_flags(xs + 2, yef, 1);
+        }
+        cp_async_wait<D>();
+        __syncthreads();
+        fl_nxt[0] = decode(rf_m1, yb, 0), fl_nxt[1] = decode(rf_m1, yb, 1);
+        psi_column(xs - 1, decode(re_m1, yef, 0) & e_mask, fl_nxt, g_cur, pm, pm_lo, pm_hi);
+        __syncthreads();
+        prefetch(xs - 1);
+        cp_async_wait<D>();
+        __syncthreads();
+        fl_cur[0] = decode(rf_0, yb, 0), fl_cur[1] = decode(rf_0, yb, 1);
+        psi_column(xs, decode(re_0, yef, 0) & e_mask, fl_cur, g_cur, p0, p0_lo, p0_hi);
+    }
 
     // ---- running pointers: everything the iteration touches is pointer + immediate -----------------------
     const int dm = (yb - 1 < 0 ? yb - 1 + H : yb - 1) - yb;      // f streams with the periodic wrap (np.roll) ...
@@ -362,65 +385,63 @@ __global__ void __launch_bounds__(Cfg::NT, 3)
     const uint8_t *fr_edge = P.reflect + cell_idx(Hp, xs + 3, 0) + yef;
     const uint32_t *fs_edge = P.solid + (size_t)(xs + 3 + G) * (Hp >> 5) + (yef >> 5);
 
-    // f of the row pair of the column at `pcol` (row yb): stream + bounce-back straight into registers
-    auto load_f = [&](const T *pcol, unsigned b0bits, unsigned b1bits) {
-        const bool anyb = __any_sync(FULL, has && ((b0bits | b1bits) != 0u));
-        if (has) {
-            const T *pmn = pcol + dm, *ppl = pcol + dp;  // rows yb-1 / yb+2 (wrapped)
-            if (!anyb) {
-                f[1] = *reinterpret_cast<const p2 *>(pcol - S + 1 * Hp);
-                f[3] = *reinterpret_cast<const p2 *>(pcol + S + 3 * Hp);
-                f[2] = mk(pmn[2 * Hp], pcol[2 * Hp]);
-                f[4] = mk(pcol[4 * Hp + 1], ppl[4 * Hp]);
-                f[5] = mk(pmn[-S + 5 * Hp], pcol[-S + 5 * Hp]);
-                f[6] = mk(pmn[S + 6 * Hp], pcol[S + 6 * Hp]);
-                f[7] = mk(pcol[S + 7 * Hp + 1], ppl[S + 7 * Hp]);
-                f[8] = mk(pcol[-S + 8 * Hp + 1], ppl[-S + 8 * Hp]);
-            } else {
-                const T *o = pcol, *o1 = pcol + 1;
-                f[1] = mk(ldg_pick(pcol - S + 1 * Hp, o + 3 * Hp, b0bits & 0x01u), ldg_pick(pcol - S + 1 * Hp + 1, o1 + 3 * Hp, b1bits & 0x01u));
-                f[2] = mk(ldg_pick(pmn + 2 * Hp, o + 4 * Hp, b0bits & 0x02u), ldg_pick(pcol + 2 * Hp, o1 + 4 * Hp, b1bits & 0x02u));
-                f[3] = mk(ldg_pick(pcol + S + 3 * Hp, o + 1 * Hp, b0bits & 0x04u), ldg_pick(pcol + S + 3 * Hp + 1, o1 + 1 * Hp, b1bits & 0x04u));
-                f[4] = mk(ldg_pick(pcol + 4 * Hp + 1, o + 2 * Hp, b0bits & 0x08u), ldg_pick(ppl + 4 * Hp, o1 + 2 * Hp, b1bits & 0x08u));
-                f[5] = mk(ldg_pick(pmn - S + 5 * Hp, o + 7 * Hp, b0bits & 0x10u), ldg_pick(pcol - S + 5 * Hp, o1 + 7 * Hp, b1bits & 0x10u));
-                f[6] = mk(ldg_pick(pmn + S + 6 * Hp, o + 8 * Hp, b0bits & 0x20u), ldg_pick(pcol + S + 6 * Hp, o1 + 8 * Hp, b1bits & 0x20u));
-                f[7] = mk(ldg_pick(pcol + S + 7 * Hp + 1, o + 5 * Hp, b0bits & 0x40u), ldg_pick(ppl + S + 7 * Hp, o1 + 5 * Hp, b1bits & 0x40u));
-                f[8] = mk(ldg_pick(pcol - S + 8 * Hp + 1, o + 6 * Hp, b0bits & 0x80u), ldg_pick(ppl - S + 8 * Hp, o1 + 6 * Hp, b1bits & 0x80u));
-            }
-            f[0] = ldg_v2(pcol);
-        }
-    };
-
-    // ---- warm-up: g columns xs-2 .. xs+1, psi of columns xs-1 and xs, f of column xs, flags up to xs+2 ------
-    for (int v = xs - 4 - D; v < xs - 1; ++v) prefetch(v);
-    {
-        const RawFlags rf_m1 = load_flags(xs - 1, yb, nv), re_m1 = edge ? load_flags(xs - 1, yef, 1) : z;
-        const RawFlags rf_0 = load_flags(xs, yb, nv), re_0 = edge ? load_flags(xs, yef, 1) : z;
-        const RawFlags rf_1 = load_flags(xs + 1, yb, nv), re_1 = edge ? load_flags(xs + 1, yef, 1) : z;
-        rq = load_flags(xs + 2, yb, nv);
-        if (edge) re = load_flags(xs + 2, yef, 1);
-        cp_async_wait<D>();
-        __syncthreads();
-        fl_nxt[0] = decode(rf_m1, yb, 0), fl_nxt[1] = decode(rf_m1, yb, 1);
-        psi_column(xs - 1, decode(re_m1, yef, 0) & e_mask, fl_nxt, g_cur, pm, pm_lo, pm_hi);
-        __syncthreads();
-        prefetch(xs - 1);
-        cp_async_wait<D>();
-        __syncthreads();
-        fl_cur[0] = decode(rf_0, yb, 0), fl_cur[1] = decode(rf_0, yb, 1);
-        psi_column(xs, decode(re_0, yef, 0) & e_mask, fl_cur, g_cur, p0, p0_lo, p0_hi);
-        fl_nxt[0] = decode(rf_1, yb, 0), fl_nxt[1] = decode(rf_1, yb, 1);
-        fe_nxt = decode(re_1, yef, 0) & e_mask;
-        load_f(pc, fl_cur[0] & 0xffu, fl_cur[1] & 0xffu);
-    }
-
-    // Iteration x: psi of column x+1 from the stages; collide + store column x, whose f was loaded ONE ITERATION
-    // EARLIER (a whole barrier + psi phase hides the memory latency; no extra registers: the loads of column x+1
-    // go into the registers the stores of column x have just released).
     for (int x = xs; x < xe; ++x) {
         cp_async_wait<D - 1>();  // g column x+2 has landed
         __syncthreads();         // ... for every thread; and everybody is done with iteration x-1
+        // decode the flags of column x+1 before any new global load is issued (see k_fused)
+        unsigned fe_nxt = decode(eq0, yef, 0) & e_mask;
+        fl_nxt[0] = decode(fq0, yb, 0), fl_nxt[1] = decode(fq0, yb, 1);
+        asm volatile("" : "+r"(fl_nxt[0]), "+r"(fl_nxt[1]), "+r"(fe_nxt)::"memory");
         prefetch(x);
+        p2 f[9];
+        {   // f of column x: stream + bounce-back straight into registers
+            const unsigned b0bits = fl_cur[0] & 0xffu, b1bits = fl_cur[1] & 0xffu;
+            const bool anyb = __any_sync(FULL, has && ((b0bits | b1bits) != 0u));
+            if (has) {
+                const T *pmn = pc + dm, *ppl = pc + dp;  // rows yb-1 / yb+2 (wrapped)
+                if (!anyb) {
+                    f[1] = *reinterpret_cast<const p2 *>(pc - S + 1 * Hp);
+                    f[3] = *reinterpret_cast<const p2 *>(pc + S + 3 * Hp);
+                    f[2] = mk(pmn[2 * Hp], pc[2 * Hp]);
+                    f[4] = mk(pc[4 * Hp + 1], ppl[4 * Hp]);
+                    f[5] = mk(pmn[-S + 5 * Hp], pc[-S + 5 * Hp]);
+                    f[6] = mk(pmn[S + 6 * Hp], pc[S + 6 * Hp]);
+                    f[7] = mk(pc[S + 7 * Hp + 1], ppl[S + 7 * Hp]);
+                    f[8] = mk(pc[-S + 8 * Hp + 1], ppl[-S + 8 * Hp]);
+                } else {
+                    const T *o = pc, *o1 = pc + 1;
+                    f[1] = mk(ldg_pick(pc - S + 1 * Hp, o + 3 * Hp, b0bits & 0x01u), ldg_pick(pc - S + 1 * Hp + 1, o1 + 3 * Hp, b1bits & 0x01u));
+                    f[2] = mk(ldg_pick(pmn + 2 * Hp, o + 4 * Hp, b0bits & 0x02u), ldg_pick(pc + 2 * Hp, o1 + 4 * Hp, b1bits & 0x02u));
+                    f[3] = mk(ldg_pick(pc + S + 3 * Hp, o + 1 * Hp, b0bits & 0x04u), ldg_pick(pc + S + 3 * Hp + 1, o1 + 1 * Hp, b1bits & 0x04u));
+                    f[4] = mk(ldg_pick(pc + 4 * Hp + 1, o + 2 * Hp, b0bits & 0x08u), ldg_pick(ppl + 4 * Hp, o1 + 2 * Hp, b1bits & 0x08u));
+                    f[5] = mk(ldg_pick(pmn - S + 5 * Hp, o + 7 * Hp, b0bits & 0x10u), ldg_pick(pc - S + 5 * Hp, o1 + 7 * Hp, b1bits & 0x10u));
+                    f[6] = mk(ldg_pick(pmn + S + 6 * Hp, o + 8 * Hp, b0bits & 0x20u), ldg_pick(pc + S + 6 * Hp, o1 + 8 * Hp, b1bits & 0x20u));
+                    f[7] = mk(ldg_pick(pc + S + 7 * Hp + 1, o + 5 * Hp, b0bits & 0x40u), ldg_pick(ppl + S + 7 * Hp, o1 + 5 * Hp, b1bits & 0x40u));
+                    f[8] = mk(ldg_pick(pc - S + 8 * Hp + 1, o + 6 * Hp, b0bits & 0x80u), ldg_pick(ppl - S + 8 * Hp, o1 + 6 * Hp, b1bits & 0x80u));
+                }
+                f[0] = ldg_v2(pc);
+            }
+        }
+        {   // the lines of f column x+L2_AHEAD into L2: one prefetch per 128-byte line of the strip
+            constexpr int LPP = (ROWS * (int)sizeof(T) + 127) / 128;
+            const int cf = x + FUSED_L2_AHEAD;
+            const int tt = NT - 1 - t;  // the cp.async issue above kept the low warps busy: use the high ones
+            if (FUSED_L2_AHEAD > 0 && tt < 9 * LPP && cf <= xe + 1) {
+                const int pop = tt / LPP, ln = tt - pop * LPP;
+                const int yy = y0 + ln * (128 / (int)sizeof(T));
+                if (yy < H) prefetch_l2(P.src + lat_idx(Hp, cf, pop, yy));
+            }
+        }
+        // flags of column x+3 (decoded two iterations from now); the flag arrays carry one spare column
+        RawFlags fq2 = z, eq2 = z;
+        if (has) {
+            fq2.refl = *reinterpret_cast<const unsigned short *>(fr_own);
+            fq2.word = *fs_own;
+        }
+        if (edge) {
+            eq2.refl = *fr_edge;
+            eq2.word = *fs_edge;
+        }
         {
             p2 gd[9];  // dropped (see psi_column)
             psi_column(x + 1, fe_nxt, fl_nxt, gd, pp, pp_lo, pp_hi);
@@ -459,39 +480,6 @@ __global__ void __launch_bounds__(Cfg::NT, 3)
                 }
             }
         }
-        // decode the flags of column x+2 BEFORE any new global load is issued: scoreboards are shared, decoding
-        // them later would wait for the loads below as well (see k_fused)
-        unsigned fl_nn0 = decode(rq, yb, 0), fl_nn1 = decode(rq, yb, 1), fe_nn = decode(re, yef, 0) & e_mask;
-        asm volatile("" : "+r"(fl_nn0), "+r"(fl_nn1), "+r"(fe_nn)::"memory");
-        pc += S, pd += S;
-        if (x + 1 < xe) load_f(pc, fl_nxt[0] & 0xffu, fl_nxt[1] & 0xffu);  // f of column x+1
-        {   // the lines of the f column L2_AHEAD columns further on into L2: one prefetch per 128-byte line of the strip
-            constexpr int LPP = (ROWS * (int)sizeof(T) + 127) / 128;
-            const int cf = x + 1 + FUSED_L2_AHEAD;
-            const int tt = NT - 1 - t;  // the cp.async issue above kept the low warps busy: use the high ones
-            if (FUSED_L2_AHEAD > 0 && tt < 9 * LPP && cf <= xe + 1) {
-                const int pop = tt / LPP, ln = tt - pop * LPP;
-                const int yy = y0 + ln * (128 / (int)sizeof(T));
-                if (yy < H) prefetch_l2(P.src + lat_idx(Hp, cf, pop, yy));
-            }
-            // ... and of the g column that goes into the stage ring FDLBM_F32_L2G iterations from now
-            const int cgl = x + 2 + D + FDLBM_F32_L2G;
-            if (FDLBM_F32_L2G > 0 && t < 9 * LPP && cgl <= xe + 1) {
-                const int pop = t / LPP, ln = t - pop * LPP;
-                const int yy = y0 + ln * (128 / (int)sizeof(T));
-                if (yy < H) prefetch_l2(P.src + lat_idx(Hp, cgl, 9 + pop, yy));
-            }
-        }
-        // raw flags of column x+3; the flag arrays carry one spare column
-        rq = z, re = z;
-        if (has) {
-            rq.refl = *reinterpret_cast<const unsigned short *>(fr_own);
-            rq.word = *fs_own;
-        }
-        if (edge) {
-            re.refl = *fr_edge;
-            re.word = *fs_edge;
-        }
         {   // g of column x+1 for the next iteration's collision (the stages x .. x+2 are still in place)
             const unsigned b0bits = fl_nxt[0] & 0xffu, b1bits = fl_nxt[1] & 0xffu;
             const bool anyb = __any_sync(FULL, has && ((b0bits | b1bits) != 0u));
@@ -500,7 +488,9 @@ __global__ void __launch_bounds__(Cfg::NT, 3)
         pm = p0, p0 = pp;
         pm_lo = p0_lo, pm_hi = p0_hi, p0_lo = pp_lo, p0_hi = pp_hi;
         fl_cur[0] = fl_nxt[0], fl_cur[1] = fl_nxt[1];
-        fl_nxt[0] = fl_nn0, fl_nxt[1] = fl_nn1, fe_nxt = fe_nn;
+        fq0 = fq1, fq1 = fq2;
+        eq0 = eq1, eq1 = eq2;
+        pc += S, pd += S;
         fr_own += Hp, fr_edge += Hp;
         fs_own += Hp >> 5, fs_edge += Hp >> 5;
     }
