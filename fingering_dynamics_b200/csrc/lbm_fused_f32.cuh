@@ -27,6 +27,10 @@
 // (ptxas makes the loop head wait for every global load still in flight, so the stall only moves there); f one
 // column ahead in its own registers with g reloaded from a five-stage ring -4 %; L2 prefetch of f 4 columns ahead
 // -13 %, of g 4 columns ahead -9 %; eight g stages (2 CTAs/SM) -4 %.  Keep the loads late and the ring short.
+// A variant with warp-interleaved rows (lane l owns rows l and l+32: every access 128 contiguous bytes, no shared
+// memory bank conflicts, packed stencils, but two 4-byte stores per population) measured -4 % as well.
+// A skeleton of this kernel with the arithmetic replaced by delays (gpurun_in/micro/skeleton.cu) moves 6.0-6.4 TB/s:
+// the remaining gap to the copy ceiling is the per-warp dependency chain at 12 warps/SM, not the request stream.
 #pragma once
 #include "lbm_fused_vec.cuh"
 

@@ -343,7 +343,7 @@ inline int launch_fused_auto<float>(const LbmParams<float> &P, cudaStream_t stre
         const char *v = getenv("FDLBM_F32_KERNEL");
         return v && strcmp(v, "vec") == 0;
     }();
-    if (P.H % 2 == 0 && !force_vec && f32p::applicable(P)) return f32p::launch(P, stream);
+    if (!force_vec && f32p::applicable(P)) return f32p::launch(P, stream);
     return launch_fused_vec<float, FUSED_TY, 2>(P, stream);
 #else
     return launch_fused<float>(P, stream);
