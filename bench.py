@@ -132,7 +132,10 @@ def reference_arm(args):
     line = {"impl": "reference", "metric": "MLUPS (two-phase D2Q9)", "value": v, "unit": "MLUPS", "n_gpus": args.gpus,
             "steps": steps, "warmup": warm, "ms_per_step": dt / steps * 1e3, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": {"workload": "synthetic porous 8192x2048 (fingering_periodic step), CPU arm on a %dx%d crop" % (Ws, Hs)},
+            "config": {"workload": "synthetic random-block porous medium %dx%d (W x H), fingering_periodic step variant"
+                                   % (W_PER_GPU * max(1, args.gpus), H_DEFAULT), "grid_W": W_PER_GPU * max(1, args.gpus),
+                       "grid_H": H_DEFAULT, "obstacles": "circles r 8-12 on a jittered 40-pitch lattice, seed 1234",
+                       "cpu_sample": "each step runs on a %dx%d crop of the workload (same generator, same H)" % (Ws, Hs)},
             "cpu_baseline": {"value": v, "unit": "MLUPS", "cores": cores, "kind": "port",
                              "sample": "%d steps of a %dx%d crop of the workload, oracle/fd_oracle.c with OpenMP" % (steps, Ws, Hs)},
             "e2e": {"value": v, "unit": "MLUPS", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}

@@ -188,3 +188,56 @@ def test_peer_halo_engines_are_bit_identical_to_the_single_slab_run(golden, name
             assert np.array_equal(got[k], want[k][..., x0:x1]), (name, r, k)
     for e in engs:
         e.close()
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("dtype", ["f64", "f32"])
+@pytest.mark.parametrize("periodic", [False, True])
+def test_peer_halo_slabs_of_a_porous_grid_match_the_single_slab_run(dtype, periodic):
+    """256 x 192 synthetic porous medium in three slabs of 64 columns with the halo exchange fused into the step kernel:
+    same bits as one engine, for fp64 (k_fused) and for fp32 (the packed two-row kernel: its peer stores, its face CTAs
+    on the first / last slab only, marching CTAs that start at a slab edge)."""
+    from fingering_dynamics_b200 import Engine, synthetic as syn
+    from fingering_dynamics_b200.slab import slab_bounds
+    H, W, nslab = 256, 192, 3
+    c = syn.fp_constants(H)
+    solid, refl = syn.porous_geometry(H, W)
+    st = syn.fp_initial_state(solid, c)
+    kw = dict(tau=c["tau"], gamma=c["gamma"], a=c["a"], kappa=c["kappa"], Eta_n=c["Eta_n"], M=c["M"], psi_wall=c["psi_wall"],
+              dtype=dtype)
+    if periodic:
+        kw.update(zou_he="none", x_periodic=True)
+    else:
+        kw.update(zou_he="fp", inlet_ux=c["inlet_ux"], outlet_ux=c["outlet_ux"])
+    ref = Engine(H, W, **kw)
+    ref.set_geometry(solid, refl)
+    ref.set_state(**st)
+    ref.step(12)
+    want = ref.get_state(("f", "g", "psi", "rho", "ux", "uy"))
+    ref.close()
+
+    engs = [Engine(H, W, slab=slab_bounds(W, nslab, r), external_halo=True, **kw) for r in range(nslab)]
+    for e in engs:
+        e.set_geometry(solid, refl)
+    infos = [e.peer_export() for e in engs]
+    for r, e in enumerate(engs):
+        left = r - 1 if r > 0 else (nslab - 1 if periodic else None)
+        right = r + 1 if r < nslab - 1 else (0 if periodic else None)
+        if left is not None:
+            e.peer_attach(0, infos[left])
+        if right is not None:
+            e.peer_attach(1, infos[right])
+    for e in engs:
+        e.set_state(**st)
+    for e in engs:
+        e.sync()
+    for n in (1, 4, 7):
+        for e in engs:
+            e.step(n)
+    for r, e in enumerate(engs):
+        x0, x1 = slab_bounds(W, nslab, r)
+        got = e.get_state(("f", "g", "psi", "rho", "ux", "uy"))
+        for k in got:
+            assert np.array_equal(got[k], want[k][..., x0:x1]), (dtype, periodic, r, k)
+    for e in engs:
+        e.close()
