@@ -163,6 +163,15 @@ def test_config1_full_grid_against_oracle_and_reference_scalars(golden):
     assert abs(got["rho"][mask].sum() - float(d["s1000_sum_rho"])) <= 1e-10 * float(d["s1000_sum_rho"])
     for k in ("psi", "rho", "ux", "uy"):
         assert hp.rel_err(got[k][::5, ::5], d["s1000_%s_sub" % k]) <= TOL64, k
+    # ... and the reference's full default run, MAX_T = 4000 (fingering_periodic.py:17): scalars of the unmodified
+    # reference after 4000 iterations, recorded in SURVEY.md section 4 (625 s of NumPy in the build container)
+    e.step(4000 - 1000)
+    got = e.get_state(("psi", "rho", "ux", "uy"))
+    assert abs(got["psi"].sum() - (-129602.397481074615)) <= 1e-10 * 129602.4
+    assert abs(got["rho"][mask].sum() - 132092.853279157280) <= 1e-10 * 132092.9
+    assert abs(got["ux"][mask].sum() - 616.0565327062) <= 1e-9 * 616.06          # (printed with 10 decimals)
+    assert abs(got["psi"][200, 30] - 1.016953462486871) <= 1e-10
+    assert np.isfinite(got["psi"]).all() and 0.93 < got["rho"][mask].min() and got["rho"][mask].max() < 1.11
     e.close()
 
 
