@@ -157,22 +157,26 @@ FDLBM_DI void collide2(const LbmParams<float> &P, const Macro2 &m, bool solid0, 
         g[0] = fma2(omg, sub(geq, g[0]), g[0]);
     }
     const p2 n3uF = mul(uF, bc(-3.0f));
-#define FDLBM_PAIR(I, O, W, EU, EF)                                                        \
-    {                                                                                      \
-        const p2 eu = (EU), eF = (EF);                                                     \
-        const p2 A = fma2(mul(eu, bc(4.5f)), eu, nusq15);       /* 4.5 eu^2 - 1.5 u^2 */  \
-        const p2 wr = mul(m.rho, bc(W));                                                   \
-        const p2 E = fma2(wr, A, mul(p3, bc(W)));                                          \
-        const p2 Od = mul(mul(wr, bc(3.0f)), eu);                                          \
-        const p2 Fe = mul(fma2(mul(eu, bc(9.0f)), eF, n3uF), bc(W));                       \
-        const p2 Fo = mul(eF, bc(3.0f * (W)));                                             \
-        const p2 se = fma2(om, E, Fe), so = fma2(om, Od, Fo);                              \
-        f[I] = fma2(c1, f[I], add(se, so));                                                \
-        f[O] = fma2(c1, f[O], sub(se, so));                                                \
-        const p2 Eg = mul(fma2(og_psi, A, og_gm3), bc(W));                                 \
-        const p2 Og = mul(mul(og_psi, bc(3.0f * (W))), eu);                                \
-        g[I] = fma2(c1g, g[I], add(Eg, Og));                                               \
-        g[O] = fma2(c1g, g[O], sub(Eg, Og));                                               \
+    // per weight class: w rho, 3 w rho, w 3p, -3 w u.F, w om_g psi, 3 w om_g psi, w om_g 3 gamma mu
+    const p2 wr1 = mul(m.rho, bc(w1)), wr5 = mul(m.rho, bc(w5)), wr31 = mul(m.rho, bc(3.0f * w1)), wr35 = mul(m.rho, bc(3.0f * w5));
+    const p2 wp1 = mul(p3, bc(w1)), wp5 = mul(p3, bc(w5)), wF1 = mul(n3uF, bc(w1)), wF5 = mul(n3uF, bc(w5));
+    const p2 gp1 = mul(og_psi, bc(w1)), gp5 = mul(og_psi, bc(w5)), gp31 = mul(og_psi, bc(3.0f * w1)), gp35 = mul(og_psi, bc(3.0f * w5));
+    const p2 gg1 = mul(og_gm3, bc(w1)), gg5 = mul(og_gm3, bc(w5));
+#define FDLBM_PAIR(I, O, W, EU, EF)                                                                  \
+    {                                                                                                \
+        const bool ax = (W) > 0.05f;                                                                 \
+        const p2 eu = (EU), eF = (EF);                                                               \
+        const p2 A = fma2(mul(eu, bc(4.5f)), eu, nusq15);                                            \
+        const p2 E = fma2(ax ? wr1 : wr5, A, ax ? wp1 : wp5);                                        \
+        const p2 Od = mul(ax ? wr31 : wr35, eu);                                                     \
+        const p2 Fe = fma2(mul(eu, bc(9.0f * (W))), eF, ax ? wF1 : wF5);                             \
+        const p2 se = fma2(om, E, Fe), so = fma2(om, Od, mul(eF, bc(3.0f * (W))));                   \
+        f[I] = fma2(c1, f[I], add(se, so));                                                          \
+        f[O] = fma2(c1, f[O], sub(se, so));                                                          \
+        const p2 Eg = fma2(ax ? gp1 : gp5, A, ax ? gg1 : gg5);                                       \
+        const p2 Og = mul(ax ? gp31 : gp35, eu);                                                     \
+        g[I] = fma2(c1g, g[I], add(Eg, Og));                                                         \
+        g[O] = fma2(c1g, g[O], sub(Eg, Og));                                                         \
     }
     FDLBM_PAIR(1, 3, w1, m.ux, Fx)
     FDLBM_PAIR(2, 4, w1, m.uy, Fy)
@@ -396,7 +400,6 @@ __global__ void __launch_bounds__(Cfg::NT, 3)
         unsigned fe_nxt = decode(eq0, yef, 0) & e_mask;
         fl_nxt[0] = decode(fq0, yb, 0), fl_nxt[1] = decode(fq0, yb, 1);
         asm volatile("" : "+r"(fl_nxt[0]), "+r"(fl_nxt[1]), "+r"(fe_nxt)::"memory");
-        prefetch(x);
         p2 f[9];
         {   // f of column x: stream + bounce-back straight into registers
             const unsigned b0bits = fl_cur[0] & 0xffu, b1bits = fl_cur[1] & 0xffu;
@@ -426,6 +429,7 @@ __global__ void __launch_bounds__(Cfg::NT, 3)
                 f[0] = ldg_v2(pc);
             }
         }
+        prefetch(x);  // after the f loads: f is what the iteration waits for first (+0.9 %)
         {   // the lines of f column x+L2_AHEAD into L2: one prefetch per 128-byte line of the strip
             constexpr int LPP = (ROWS * (int)sizeof(T) + 127) / 128;
             const int cf = x + FUSED_L2_AHEAD;
