@@ -791,6 +791,10 @@ int fdlbm_peer_attach(fdlbm_engine *e, int side, const fdlbm_peer_info *nb)
     return 0;
 }
 
+#ifdef FDLBM_CTA_TIMES  // profiling build only (not part of include/fdlbm.h)
+int fdlbm_debug_cta_times(void *host, size_t bytes) { return (int)cudaMemcpyFromSymbol(host, fdlbm::g_cta_times, bytes); }
+#endif
+
 void *fdlbm_pinned_alloc(size_t bytes)
 {
     void *p = nullptr;

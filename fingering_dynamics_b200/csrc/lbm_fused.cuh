@@ -24,6 +24,34 @@
 
 namespace fdlbm {
 
+#ifdef FDLBM_CTA_TIMES  // profiling build (gpurun_in/cta_times.py): per-CTA start / end time, SM and strip
+__device__ unsigned long long g_cta_times[4096 * 4];
+struct CtaTimer {
+    unsigned long long t0 = 0;
+    unsigned smid = 0;
+    __device__ __forceinline__ CtaTimer()
+    {
+        if (threadIdx.x == 0) {
+            asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
+            asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
+        }
+    }
+    __device__ __forceinline__ void stop(int tag) const
+    {
+        if (threadIdx.x == 0 && blockIdx.x < 4096) {
+            unsigned long long t1;
+            asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1));
+            unsigned long long *r = g_cta_times + 4 * blockIdx.x;
+            r[0] = t0, r[1] = t1, r[2] = smid, r[3] = (unsigned long long)tag;
+        }
+    }
+};
+#else
+struct CtaTimer {
+    __device__ __forceinline__ void stop(int) const {}
+};
+#endif
+
 #ifndef FDLBM_FUSED_TY
 #define FDLBM_FUSED_TY 128
 #endif
@@ -171,6 +199,7 @@ struct RawFlags {
 template <typename T, int TY, int HPC>
 __global__ void __launch_bounds__(TY, sizeof(T) == 8 ? FDLBM_FUSED_MINB64 : FDLBM_FUSED_MINB32) k_fused(const __grid_constant__ LbmParams<T> P, int nyt, int chunk)
 {
+    const CtaTimer timer;
     using C = FusedCfg<T, TY>;
     constexpr int D = FUSED_D, NS = C::NS, PT = C::PT, HALO = C::HALO, FAM = C::FAM;
     constexpr unsigned FULL = 0xffffffffu;
@@ -385,6 +414,7 @@ __global__ void __launch_bounds__(TY, sizeof(T) == 8 ? FDLBM_FUSED_MINB64 : FDLB
         eq0 = eq1, eq1 = eq2;
     }
     cp_async_wait<0>();
+    timer.stop(yt);
 }
 
 // Column chunk length for `nyt` strips on `n_cta` resident CTA slots.  With c chunks per strip the kernel takes

@@ -1,3 +1,7 @@
+"""Per-CTA timing of the fused step kernels (profiles/README.md).  Build the instrumented library first (here, no GPU needed):
+    nvcc -gencode arch=compute_100a,code=sm_100a -O3 -std=c++17 --shared -Xcompiler -fPIC -DFDLBM_CTA_TIMES \
+         -o gpurun_in/variants/lib_dbg.so fingering_dynamics_b200/csrc/fdlbm.cu
+then on the GPU box:  python gpurun_in/cta_times.py f64|f32"""
 import ctypes, os, sys, json, numpy as np
 sys.path.insert(0, os.getcwd())
 os.environ["FDLBM_LIB"] = os.path.join(os.getcwd(), "gpurun_in/variants/lib_dbg.so")
