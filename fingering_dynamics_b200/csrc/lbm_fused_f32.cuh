@@ -21,8 +21,8 @@
 //
 // Requires an even grid height (aligned row pairs); odd heights use k_fused_vec.
 //
-// Measured on B200 (8192x2048, same box, two interleaved repetitions; profiles/README.md): this kernel 37.9 GLUPS
-// (83 % of the HBM roofline; the access pattern itself copies at 93.5 % of memcpy speed, gpurun_in/micro/pattern.cu).
+// Measured on B200 (8192x2048, same box, two interleaved repetitions; profiles/README.md): this kernel 37.9 GLUPS at
+// the time of these experiments (83 % of the HBM roofline, 38.9 = 85.4 % since; the access pattern itself copies at 93.5 % of memcpy speed, gpurun_in/micro/pattern.cu).
 // Variants that put MORE memory requests in flight were all slower: f loads issued one column ahead -1.6 %
 // (ptxas makes the loop head wait for every global load still in flight, so the stall only moves there); f one
 // column ahead in its own registers with g reloaded from a five-stage ring -4 %; L2 prefetch of f 4 columns ahead
