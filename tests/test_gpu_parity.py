@@ -258,6 +258,33 @@ def test_fp32_interface_position(golden):
     assert pp.interface_shift(out["f32"], d["s40_psi"]) <= 1e-3          # stated fp32 effect: < 0.001 cell
 
 
+def test_fp32_full_default_run_of_config1_stays_on_the_fp64_interface(golden):
+    """config 1 at the reference's full default length (400x400, 4000 iterations), fp32 engine vs fp64 engine (which
+    matches the reference to 1e-10, see above).  Measured (gpurun_in/f32_config1.py): max|dpsi| 6.1e-4, max|drho| 2.4e-5,
+    max|du|/u0 1.4e-4, the psi = 0 crossings move by 1.7e-3 cells.  Stated bounds: 3x that."""
+    from fingering_dynamics_b200 import Engine, geometry as geo, postprocess as pp
+    d = golden("fp_full_scalars")
+    H, W, mask, cls, P, s0 = _fp_full_inputs(d)
+    out = {}
+    for dt in ("f64", "f32"):
+        e = Engine(H, W, tau=P.tau, gamma=P.gamma, a=P.a, kappa=P.kappa, Eta_n=P.Eta_n, M=P.M, psi_wall=P.psi_wall,
+                   zou_he="fp", inlet_ux=d["inlet_ux"], outlet_ux=d["inlet_ux"], dtype=dt)
+        e.set_geometry(~mask, geo.reflect_bits_circle(cls[0:4], cls[4:8], cls[8:12]))
+        e.set_state(f=s0["f"], g=s0["g"], psi=s0["psi"], rho=s0["rho"], ux=s0["ux"], uy=s0["uy"], p=s0["p"], mu=s0["mu"],
+                    mix_tau=s0["mix_tau"], nabla_psix=s0["gx"], nabla_psiy=s0["gy"], nabla_psi2=s0["lap"])
+        e.step(4000)
+        out[dt] = e.get_state(("psi", "rho", "ux", "uy"))
+        e.close()
+    a, b = out["f32"], out["f64"]
+    u0 = float(np.max(d["inlet_ux"]))
+    assert np.abs(a["psi"] - b["psi"]).max() <= 2e-3
+    assert np.abs(a["rho"] - b["rho"])[mask].max() <= 1e-4
+    assert max(np.abs(a["ux"] - b["ux"])[mask].max(), np.abs(a["uy"] - b["uy"])[mask].max()) <= 5e-4 * u0
+    assert pp.interface_shift(np.where(mask, a["psi"], -1.0), np.where(mask, b["psi"], -1.0)) <= 5e-3   # cells
+    clear = (np.abs(b["psi"]) > 1e-3) & mask
+    assert np.array_equal(np.sign(a["psi"][clear]), np.sign(b["psi"][clear]))
+
+
 def test_wettability_sweep_orders_the_contact_angles(monkeypatch):
     """validation.py at its shipped size (200x250, droplet r=36 on the bottom wall) for three wall
     wettabilities: the less the wall repels the droplet phase, the smaller the contact angle."""
