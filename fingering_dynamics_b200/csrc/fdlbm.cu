@@ -409,7 +409,18 @@ int get_state_t(fdlbm_engine *e, int col0, int ncw, const fdlbm_fields *out)
         psi = (const T *)e->psi[e->pcur];
     } else {
         if (e->peer_mode() && (rc = peer_wait(e, e->peer_step))) return rc;
-        if ((rc = launch_step<T>(e, true))) return rc;  // writes lat[1-cur], psi[1-pcur], fields; no swap
+        const bool only_psi = out->psi && !out->f && !out->g && !out->rho && !out->ux && !out->uy && !out->p && !out->mu &&
+                              !out->mix_tau && !out->nabla_psix && !out->nabla_psiy && !out->nabla_psi2;
+        if (only_psi) {
+            // a psi frame (the drivers' snapshots, fingering.py:565-566): the psi pass alone, on the owned columns
+            LbmParams<T> P = make_params<T>(e, e->cur, e->pcur);
+            if (e->cfg.x_periodic && !e->cfg.external_halo && (rc = wrap_ghosts(e, e->lat[e->cur]))) return rc;
+            k_psi<T><<<cell_grid(e, e->Wl), TPB, 0, e->stream>>>(P, 0);
+            CU(cudaGetLastError());
+            e->launches += 1;
+        } else if ((rc = launch_step<T>(e, true))) {  // writes lat[1-cur], psi[1-pcur], fields; no swap
+            return rc;
+        }
         lat = (const T *)e->lat[1 - e->cur];
         psi = (const T *)e->psi[1 - e->pcur];
     }

@@ -243,6 +243,23 @@ def test_checkpoint_restart_is_bit_exact_and_watchdog_fires(golden):
     e3.close()
 
 
+@pytest.mark.parametrize("name", ["fp_small", "fg_small", "va_small"])
+def test_psi_frame_equals_the_psi_of_a_full_read_back(golden, name):
+    """get_state(("psi",)) -- the drivers' frame snapshots -- runs the psi pass only: same bits as the full finalize,
+    and the run continues undisturbed"""
+    d = golden(name)
+    e = hp.ENGINES[name](d)
+    e.set_state(**hp.state_for_engine(d, "s0"))
+    e.step(7)
+    frame = e.get_state(("psi",))["psi"]
+    full = e.get_state(("psi", "rho", "f"))
+    assert np.array_equal(frame, full["psi"])
+    e.step(3)
+    frame10 = e.get_state(("psi",))["psi"]
+    assert hp.rel_err(frame10, d["s10_psi"]) <= TOL64
+    e.close()
+
+
 def test_fp32_interface_position(golden):
     """fp32 vs fp64 on the wettability case: displacement of the interface (psi = 0 crossings)"""
     from fingering_dynamics_b200 import postprocess as pp
