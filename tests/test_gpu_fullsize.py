@@ -99,11 +99,11 @@ def test_fused_equals_twopass_on_random_geometry_and_odd_sizes(variant, H, W):
 
 @pytest.mark.parametrize("variant", ["fp", "fg", "va"])
 @pytest.mark.parametrize("H,W", [(4, 33), (64, 40), (66, 40), (128, 33), (130, 96), (194, 20), (256, 64), (258, 50), (320, 48),
-                                 (512, 37), (2048, 24)])
+                                 (512, 37), (2048, 24), (4096, 20), (8192, 20)])
 def test_fused_equals_twopass_on_random_geometry_and_even_sizes(variant, H, W):
     """even H: the fp32 engine runs the packed two-row kernel (lbm_fused_f32.cuh) -- one-lane warps at the strip tail
     (H = 66, 130, 194, 258), idle warps (64, 128, 320), strips with a wrapping apron, a second strip (258, 320, 512),
-    the compile-time row pitch (2048)"""
+    the compile-time row pitches (2048, 4096, 8192)"""
     _fused_vs_twopass(variant, H, W)
 
 
