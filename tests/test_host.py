@@ -44,6 +44,19 @@ def test_no_cpu_fallback_without_a_device():
     assert rc < 0
 
 
+def test_product_package_never_touches_the_oracle():
+    """The oracle is test infrastructure: no source of the shipped package may import, load or name it."""
+    pkg = os.path.join(ROOT, "fingering_dynamics_b200")
+    hits = []
+    for d, _, files in os.walk(pkg):
+        for fn in files:
+            if fn.endswith((".py", ".cu", ".cuh", ".h")):
+                txt = open(os.path.join(d, fn), errors="replace").read()
+                if re.search(r"oracle|libfd_oracle", txt):
+                    hits.append(os.path.relpath(os.path.join(d, fn), ROOT))
+    assert not hits, hits
+
+
 def test_config_validation_messages():
     from fingering_dynamics_b200 import _native as nat
     cfg = nat.Config()
