@@ -278,21 +278,27 @@ def save_frames(frames, path):
         pickle.dump(np.asarray(frames), fh)
 
 
-def run_loop(cm, reflect, n_steps, frames_every=0, dtype="f64"):
+def run_loop(cm, reflect, n_steps, frames_every=0, dtype="f64", check_finite=False):
     """Advance `cm` n_steps reference iterations on the GPU; returns the list of psi frames taken every
-    `frames_every` steps BEFORE the step, like fingering.py:565-566 (empty if 0)."""
+    `frames_every` steps BEFORE the step, like fingering.py:565-566 (empty if 0).  check_finite=True raises
+    FloatingPointError at the first snapshot (or at the end) that finds non-finite populations -- the stand-in
+    for the reference's np.seterr(all='raise') (fingering_periodic.py:497)."""
     eng = cm.make_engine(reflect, dtype=dtype)
     frames = []
     done = 0
     try:
         if frames_every:
             while done < n_steps:
+                if check_finite:
+                    eng.check_finite()
                 frames.append(eng.get_state(("psi",))["psi"])
                 k = min(frames_every, n_steps - done)
                 eng.step(k)
                 done += k
         else:
             eng.step(n_steps)
+        if check_finite:
+            eng.check_finite()
         cm.pull_from(eng)
     finally:
         eng.close()
