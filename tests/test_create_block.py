@@ -1,5 +1,7 @@
 """The drop-in Createblock (local-window templates) against the reference's own outputs
 (tests/golden/geometry.npz, produced by create_block.py:51-407 in the build container)."""
+import os
+
 import numpy as np
 import pytest
 
@@ -64,3 +66,58 @@ def test_default_config1_geometry_counts(golden):
     cls = np.unpackbits(d["class_bits"])[:12 * 160000].reshape(12, 400, 400).astype(bool)
     for k, m in enumerate(list(side) + list(cave) + list(vex)):
         assert np.array_equal(m, cls[k]), k
+
+
+REF_DIR = "/root/reference/lattice_boltzmann"
+
+
+@pytest.mark.skipif(not os.path.isdir(REF_DIR), reason="the reference tree only exists in the build container")
+@pytest.mark.parametrize("seed", [0, 1])
+def test_random_shape_lists_against_the_reference_itself(seed):
+    """Build-container only: random circle / ellipse / rectangle lists (overlaps, shapes on the border, lists that
+    make the reference raise) through the reference's Createblock (create_block.py:51-407) and through the twin:
+    identical outputs, or the same exception type."""
+    import importlib.util
+    import warnings
+    spec = importlib.util.spec_from_file_location("_ref_create_block", os.path.join(REF_DIR, "create_block.py"))
+    ref = importlib.util.module_from_spec(spec)
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        spec.loader.exec_module(ref)
+    rng = np.random.default_rng(seed)
+
+    def run(cls, Hh, Ww, kind, lst):
+        try:
+            with warnings.catch_warnings():
+                warnings.simplefilter("ignore")
+                cb = cls(Hh, Ww)
+                return getattr(cb, ("setCirleblock", "setEllipseblock", "setblock")[kind])(lst), None
+        except Exception as ex:  # noqa: BLE001
+            return None, type(ex).__name__
+
+    for it in range(45):
+        Hh, Ww = int(rng.integers(40, 90)), int(rng.integers(40, 90))
+        kind = it % 3
+        n = int(rng.integers(1, 5))
+        if kind == 0:
+            lst = [((int(rng.integers(0, Ww)), int(rng.integers(0, Hh))), int(rng.integers(1, 13))) for _ in range(n)]
+        elif kind == 1:
+            lst = [{"c_x": int(rng.integers(5, Ww - 5)), "c_y": int(rng.integers(5, Hh - 5)), "r_x": int(rng.integers(4, 24)),
+                    "r_y": int(rng.integers(4, 24)), "angle": int(rng.choice([0, 90, 30, 45, 120, 180]))} for _ in range(n)]
+        else:
+            lst = []
+            for _ in range(n):
+                x0, y0 = int(rng.integers(0, Ww - 3)), int(rng.integers(0, Hh - 3))
+                lst.append(((x0, y0), (int(rng.integers(x0, min(Ww, x0 + 15))), int(rng.integers(y0, min(Hh, y0 + 15))))))
+        want, wex = run(ref.Createblock, Hh, Ww, kind, lst)
+        got, gex = run(Createblock, Hh, Ww, kind, lst)
+        assert wex == gex, (kind, Hh, Ww, lst, wex, gex)
+        if wex:
+            continue
+        assert np.array_equal(want[0], got[0]), (kind, Hh, Ww, lst)
+        if kind == 2:
+            assert want[1] == got[1], (Hh, Ww, lst)
+        else:
+            for li in (1, 2, 3):
+                for k in range(4):
+                    assert np.array_equal(np.asarray(want[li][k]), np.asarray(got[li][k])), (kind, li, k, Hh, Ww, lst)
