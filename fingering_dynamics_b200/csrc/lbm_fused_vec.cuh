@@ -295,11 +295,14 @@ int launch_fused_vec(const LbmParams<T> &P, cudaStream_t stream)
 {
     using C = VecCfg<T, NT, VEC>;
     auto kern = k_fused_vec<T, NT, VEC>;
-    static int n_cta = 0;
+    // resident CTA slots, cached per device (the shared-memory attribute is a per-device setting too)
+    static int n_cta_of[64] = {0};
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess) return (int)cudaErrorInvalidDevice;
+    int &n_cta = n_cta_of[dev & 63];
     if (n_cta == 0) {
-        int dev = 0, sms = 0, occ = 0;
-        cudaError_t e = cudaGetDevice(&dev);
-        if (e != cudaSuccess) return (int)e;
+        int sms = 0, occ = 0;
+        cudaError_t e;
         e = cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
         if (e != cudaSuccess) return (int)e;
         e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::SMEM);
