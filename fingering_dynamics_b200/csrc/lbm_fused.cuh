@@ -93,6 +93,14 @@ __device__ __forceinline__ void cp_async_wait()
     asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory");
 }
 __device__ __forceinline__ void prefetch_l2(const void *p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
+// one request for a whole run of bytes (16-byte aligned, a multiple of 16 bytes) instead of one per 128-byte line
+__device__ __forceinline__ void prefetch_l2_bulk(const void *p, unsigned bytes)
+{
+    asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(p), "r"(bytes));
+}
+#ifndef FDLBM_L2_BULK
+#define FDLBM_L2_BULK 0  // 1: the f columns are prefetched into L2 with one bulk request per population
+#endif
 
 // ---- bulk asynchronous copies (the TMA engine's 1-D path, cp.async.bulk) completing on an mbarrier ----------
 __device__ __forceinline__ unsigned smem_u32(const void *p) { return (unsigned)__cvta_generic_to_shared(p); }
@@ -377,7 +385,10 @@ __global__ void __launch_bounds__(TY, sizeof(T) == 8 ? FDLBM_FUSED_MINB64 : FDLB
             constexpr int LPP = (TY * (int)sizeof(T) + 127) / 128;  // lines per population row
             const int cf = x + FUSED_L2_AHEAD;
             const int tt = TY - 1 - t;  // the cp.async issue above kept the low warps busy: use the high ones
-            if (FUSED_L2_AHEAD > 0 && tt < 9 * LPP && cf <= xe + 1) {
+            if (FDLBM_L2_BULK) {
+                if (FUSED_L2_AHEAD > 0 && tt < 9 && cf <= xe + 1)
+                    prefetch_l2_bulk(P.src + lat_idx(Hp, cf, tt, y0), (unsigned)((ny * (int)sizeof(T) + 15) & ~15));
+            } else if (FUSED_L2_AHEAD > 0 && tt < 9 * LPP && cf <= xe + 1) {
                 const int pop = tt / LPP, ln = tt - pop * LPP;
                 const int yy = y0 + ln * (128 / (int)sizeof(T));
                 if (yy < H) prefetch_l2(P.src + lat_idx(Hp, cf, pop, yy));

@@ -439,7 +439,11 @@ __global__ void __launch_bounds__(Cfg::NT, 3)
             constexpr int LPP = (ROWS * (int)sizeof(T) + 127) / 128;
             const int cf = x + FUSED_L2_AHEAD;
             const int tt = NT - 1 - t;  // the cp.async issue above kept the low warps busy: use the high ones
-            if (FUSED_L2_AHEAD > 0 && tt < 9 * LPP && cf <= xe + 1) {
+            if (FDLBM_L2_BULK) {
+                if (FUSED_L2_AHEAD > 0 && tt < 9 && cf <= xe + 1)
+                    prefetch_l2_bulk(P.src + lat_idx(Hp, cf, tt, y0),
+                                     (unsigned)((min(ROWS, H - y0) * (int)sizeof(T) + 15) & ~15));
+            } else if (FUSED_L2_AHEAD > 0 && tt < 9 * LPP && cf <= xe + 1) {
                 const int pop = tt / LPP, ln = tt - pop * LPP;
                 const int yy = y0 + ln * (128 / (int)sizeof(T));
                 if (yy < H) prefetch_l2(P.src + lat_idx(Hp, cf, pop, yy));
