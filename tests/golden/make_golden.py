@@ -464,9 +464,9 @@ def make_fg_full():
     d = {"H": H, "W": W, "n_rects": len(rects), "n_fluid": int(mask.sum()), "mask_bits": np.packbits(mask),
          "rects": np.array([[r[0][0], r[0][1], r[1][0], r[1][1]] for r in rects])}
     d.update(consts(FG, ["tau", "gamma", "a", "kappa", "Eta_n", "M", "u0", "psi_wall"]))
-    for it in range(1, 301):
+    for it in range(1, FG.MAX_T + 1):   # the shipped run length (fingering.py:18)
         fg_iteration(cm, mask, bb, corner_list)
-        if it in (10, 100, 300):
+        if it in (10, 100, 300, FG.MAX_T):
             tag = "s%d" % it
             d[tag + "_sum_psi"] = np.float64(cm.psi.sum())
             d[tag + "_sum_rho"] = np.float64(cm.rho.sum())
@@ -483,9 +483,9 @@ def make_va_full():
         cm = VA.Compute()
     d = {"H": VA.H, "W": VA.W}
     d.update(consts(VA, ["tau", "gamma", "a", "kappa", "Eta_n", "M", "psi_wall", "cs", "c"]))
-    for it in range(1, 501):
+    for it in range(1, VA.MAX_T + 1):   # the shipped run length (validation.py:16)
         va_iteration(cm)
-        if it in (10, 100, 500):
+        if it in (10, 100, 500, VA.MAX_T):
             tag = "s%d" % it
             d[tag + "_sum_psi"] = np.float64(cm.psi.sum())
             d[tag + "_sum_rho"] = np.float64(cm.rho.sum())

@@ -126,7 +126,8 @@ def test_fingering_periodic_main_default_geometry(golden):
 
 
 def test_fingering_shipped_configuration_against_reference_scalars(golden):
-    """config 3 as shipped (fingering.py: 380x380, 40 squares, np.random.seed(0)) for 300 iterations,
+    """config 3 as shipped (fingering.py: 380x380, 40 squares, np.random.seed(0)) over its full default run
+    (MAX_T = 1000, fingering.py:18),
     twin drivers + engine against the reference's own numbers (tests/golden/make_golden.py --full23)."""
     from fingering_dynamics_b200.lattice_boltzmann import fingering as FG, _compute
     from fingering_dynamics_b200.lattice_boltzmann.create_block import Createblock
@@ -141,7 +142,7 @@ def test_fingering_shipped_configuration_against_reference_scalars(golden):
     cm = FG.Compute(mask)
     eng = cm.make_engine(FG.reflect_bits(corner_list))
     done = 0
-    for step in (10, 100, 300):
+    for step in (10, 100, 300, FG.MAX_T):
         eng.step(step - done)
         done = step
         st = eng.get_state(("psi", "rho", "ux", "uy"))
@@ -154,7 +155,8 @@ def test_fingering_shipped_configuration_against_reference_scalars(golden):
 
 
 def test_validation_shipped_configuration_against_reference_scalars(golden):
-    """config 2 as shipped (validation.py: 200x250 droplet, psi_wall = 0) for 500 iterations."""
+    """config 2 as shipped (validation.py: 200x250 droplet, psi_wall = 0) over its full default run (MAX_T = 1000,
+    validation.py:16)."""
     from fingering_dynamics_b200 import geometry as geo
     from fingering_dynamics_b200.lattice_boltzmann import validation as VA
     d = golden("va_full_scalars")
@@ -162,7 +164,7 @@ def test_validation_shipped_configuration_against_reference_scalars(golden):
     cm = VA.Compute()
     eng = cm.make_engine(geo.reflect_bits_wall_rows(VA.H, VA.W, 0, VA.H - 1))
     done = 0
-    for step in (10, 100, 500):
+    for step in (10, 100, 500, VA.MAX_T):
         eng.step(step - done)
         done = step
         st = eng.get_state(("psi", "rho", "ux", "uy"))

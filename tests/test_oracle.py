@@ -112,3 +112,67 @@ def test_initial_states_bit_exact(golden):
         assert np.array_equal(s[k], d["s0_" + k]), k
     for k in ("rho", "ux", "uy", "p", "mu", "mix_tau"):
         assert np.array_equal(np.where(m, s[k], 0.0), d["s0_" + k]), k
+
+
+def _bits(d, key, shape):
+    return np.unpackbits(d[key])[:int(np.prod(shape))].reshape(shape).astype(bool)
+
+
+def test_config1_shipped_size_1000_iterations_bit_exact(golden):
+    """fingering_periodic.py as shipped (400x400, 90 circles): the oracle from its own restated initial state against
+    the reference's sums and subsampled fields at iterations 1, 10, 100, 1000 -- bit for bit."""
+    d = golden("fp_full_scalars")
+    H, W = int(d["H"]), int(d["W"])
+    mask = _bits(d, "mask_bits", (H, W))
+    cls = _bits(d, "class_bits", (12, H, W)).astype(np.uint8)
+    P = hp.fp_params(d)
+    run = orc.Run(P, orc.fp_initial_state(P, mask), mask=mask, circ_masks=cls, zou_he=1, inlet_ux=d["inlet_ux"],
+                  outlet_ux=d["inlet_ux"])
+    done = 0
+    for step in (1, 10, 100, 1000):
+        a = run.iterate(step - done)
+        done = step
+        tag = "s%d" % step
+        assert a["psi"].sum() == float(d[tag + "_sum_psi"]), step
+        assert a["rho"][mask].sum() == float(d[tag + "_sum_rho"]), step
+        assert a["psi"][200, 30] == float(d[tag + "_psi_200_30"]), step
+        assert np.array_equal(a["psi"][::5, ::5], d[tag + "_psi_sub"]), step
+        for k in ("rho", "ux", "uy"):
+            assert np.array_equal(np.where(mask, a[k], 0.0)[::5, ::5], d["%s_%s_sub" % (tag, k)]), (step, k)
+
+
+def test_config3_shipped_size_full_run_bit_exact(golden):
+    """fingering.py as shipped (380x380, 40 squares, np.random.seed(0), MAX_T = 1000): the oracle from its restated
+    initial state (the two RNG draws of fingering.py:106-107 replayed) against the reference, bit for bit."""
+    from fingering_dynamics_b200.lattice_boltzmann.create_block import Createblock
+    d = dict(golden("fg_full_scalars"))
+    H, W = int(d["H"]), int(d["W"])
+    mask = _bits(d, "mask_bits", (H, W))
+    rects = [((int(r[0]), int(r[1])), (int(r[2]), int(r[3]))) for r in d["rects"]]
+    bpa, corners = Createblock(H, W).setblock(rects)
+    assert np.array_equal(bpa != 1, mask)
+    d["mask"] = mask
+    d["corners"] = np.array([[c["top_left"][0], c["top_left"][1], c["bottom_left"][0], c["bottom_left"][1],
+                              c["top_right"][0], c["top_right"][1], c["bottom_right"][0], c["bottom_right"][1]]
+                             for c in corners])
+    state = np.random.get_state()
+    try:
+        np.random.seed(0)
+        sign = np.random.randint(0, 1, size=(H, W)) * 2 - 1.0
+        rho = np.ones((H, W)) + np.random.rand(H, W) * 0.001 * sign
+    finally:
+        np.random.set_state(state)
+    P = hp.fg_params(d)
+    u = np.full(H, float(d["c_u0"]))
+    run = orc.Run(P, orc.fg_initial_state(P, mask, np.where(mask, rho, 1.0)), mask=mask, rect_corners=d["corners"],
+                  wall_rows=(1, H - 2), zou_he=2, inlet_ux=u, outlet_ux=u)
+    done = 0
+    for step in (10, 100, 300, 1000):
+        a = run.iterate(step - done)
+        done = step
+        tag = "s%d" % step
+        assert a["psi"].sum() == float(d[tag + "_sum_psi"]), step
+        assert a["rho"][mask].sum() == float(d[tag + "_sum_rho"]), step
+        assert np.array_equal(a["psi"][::5, ::5], d[tag + "_psi_sub"]), step
+        for k in ("rho", "ux", "uy"):
+            assert np.array_equal(np.where(mask, a[k], 0.0)[::5, ::5], d["%s_%s_sub" % (tag, k)]), (step, k)
