@@ -75,7 +75,7 @@ class AlgebraOut(ctypes.Structure):
 class PeerInfo(ctypes.Structure):
     """fdlbm_peer_info of include/fdlbm.h (plain bytes: can be pickled and sent to another rank)"""
     _fields_ = [("pid", ctypes.c_int64), ("device", ctypes.c_int32), ("Wl", ctypes.c_int32), ("Hp", ctypes.c_int32),
-                ("dtype", ctypes.c_int32), ("lat", ctypes.c_void_p * 2), ("flags", ctypes.c_void_p),
+                ("dtype", ctypes.c_int32), ("H", ctypes.c_int32), ("lat", ctypes.c_void_p * 2), ("flags", ctypes.c_void_p),
                 ("ipc_lat", (ctypes.c_ubyte * 64) * 2), ("ipc_flags", ctypes.c_ubyte * 64)]
 
 

@@ -756,6 +756,7 @@ int fdlbm_peer_export(fdlbm_engine *e, fdlbm_peer_info *out)
     out->Wl = e->Wl;
     out->Hp = e->Hp;
     out->dtype = e->cfg.dtype;
+    out->H = e->cfg.H;
     out->lat[0] = e->lat[0];
     out->lat[1] = e->lat[1];
     out->flags = e->flags;
@@ -770,7 +771,8 @@ int fdlbm_peer_attach(fdlbm_engine *e, int side, const fdlbm_peer_info *nb)
 {
     if (!e || !nb || (side != 0 && side != 1)) return fail(FDLBM_E_ARG, "bad argument");
     if (!e->cfg.external_halo) return fail(FDLBM_E_ARG, "peer halos need an engine created with external_halo=1");
-    if (nb->Hp != e->Hp || nb->dtype != e->cfg.dtype) return fail(FDLBM_E_ARG, "neighbour has a different H or dtype");
+    if (nb->H != e->cfg.H || nb->Hp != e->Hp || nb->dtype != e->cfg.dtype)
+        return fail(FDLBM_E_ARG, "neighbour has a different H or dtype");
     if (e->peer_flags[side]) return fail(FDLBM_E_STATE, "side %d is already attached", side);
     CU(cudaSetDevice(e->cfg.device));
     int rc = load_stream_memops();

@@ -145,7 +145,7 @@ int fdlbm_count_nonfinite(fdlbm_engine *e, int64_t *n_bad);
  *   fdlbm_peer_attach: side 0 = `nb` owns the columns just below x0, side 1 = just above x1. */
 typedef struct {
     int64_t pid;                /* process that owns the memory */
-    int32_t device, Wl, Hp, dtype;
+    int32_t device, Wl, Hp, dtype, H;
     void *lat[2], *flags;       /* valid inside process `pid` */
     unsigned char ipc_lat[2][64], ipc_flags[64]; /* cudaIpcMemHandle_t */
 } fdlbm_peer_info;

@@ -152,9 +152,10 @@ def test_slab_engines_refuse_multi_step_calls_without_attached_neighbours(golden
     with pytest.raises(nat.FdlbmError) as ei:
         e.step(2)
     assert "one step per call" in str(ei.value)
-    other = hp.fp_engine(golden("fp_small"), dtype="f32")
-    info = nat.PeerInfo.from_buffer_copy(other.peer_export())
-    assert nat.lib().fdlbm_peer_attach(e._h, 1, ctypes.byref(info)) == E_ARG   # different row pitch and dtype
-    assert b"different H" in nat.lib().fdlbm_last_error()
-    other.close()
+    for other in (hp.fp_engine(golden("fp_small"), dtype="f32"),   # different row pitch and dtype
+                  hp.fg_engine(golden("fg_small"))):               # H = 36 against 48: same padded row pitch (64)
+        info = nat.PeerInfo.from_buffer_copy(other.peer_export())
+        assert nat.lib().fdlbm_peer_attach(e._h, 1, ctypes.byref(info)) == E_ARG
+        assert b"different H" in nat.lib().fdlbm_last_error()
+        other.close()
     e.close()

@@ -198,3 +198,29 @@ def test_step_kernels_keep_their_register_budget():
     for name, (reg, stack) in fused.items():
         assert reg <= 168, (name, reg)
         assert stack == 0, (name, stack)
+
+
+def test_ctypes_structures_match_the_header_layout(tmp_path):
+    """sizeof / offsetof of every struct of include/fdlbm.h as gcc sees them == the ctypes mirrors in _native.py."""
+    import subprocess
+    from fingering_dynamics_b200 import _native as nat
+    pairs = {"fdlbm_config": nat.Config, "fdlbm_fields": nat.Fields, "fdlbm_halo": nat.Halo,
+             "fdlbm_peer_info": nat.PeerInfo, "fdlbm_algebra_out": nat.AlgebraOut}
+    lines = ['#include "%s"' % os.path.join(ROOT, "include", "fdlbm.h"), "#include <stdio.h>", "int main(void){"]
+    for cname, cls in pairs.items():
+        lines.append('printf("%s %%zu", sizeof(%s));' % (cname, cname))
+        for fname, *_ in cls._fields_:
+            lines.append('printf(" %%zu", offsetof(%s, %s));' % (cname, fname))
+        lines.append('printf("\\n");')
+    lines.append("return 0;}")
+    src = tmp_path / "layout.c"
+    src.write_text("\n".join(lines))
+    exe = tmp_path / "layout"
+    subprocess.run(["gcc", "-std=c99", str(src), "-o", str(exe)], check=True)
+    out = subprocess.run([str(exe)], check=True, capture_output=True, text=True).stdout.strip().splitlines()
+    assert len(out) == len(pairs)
+    for line in out:
+        name, size, *offs = line.split()
+        cls = pairs[name]
+        assert ctypes.sizeof(cls) == int(size), name
+        assert [getattr(cls, f[0]).offset for f in cls._fields_] == [int(o) for o in offs], name
