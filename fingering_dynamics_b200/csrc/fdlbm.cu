@@ -39,6 +39,7 @@ int fail(int code, const char *fmt, ...)
     } while (0)
 
 enum { ST_EMPTY = 0, ST_PRE = 1, ST_POST = 2 };
+constexpr int STEAL_CAP = 1 << 16;  // CTAs the work table of the stealing build has room for
 
 }  // namespace
 
@@ -66,6 +67,7 @@ struct fdlbm_engine {
     int peer_Wl[2] = {0, 0};
     bool peer_ipc[2] = {false, false};
     uint32_t peer_step = 0;                                   // steps taken in peer mode (never reset)
+    int *steal_tab = nullptr;                                 // work table of the -DFDLBM_STEAL=1 build
     int cur = 0, pcur = 0;
     int state = ST_EMPTY;
     bool have_geometry = false;
@@ -115,6 +117,8 @@ LbmParams<T> make_params(const fdlbm_engine *e, int src, int psrc)
     P.f3coef = (T)c.outlet_f3_coef;
     P.peer_lo = P.peer_hi = nullptr;
     P.peer_lo_Wl = 0;
+    P.steal = nullptr;
+    P.steal_cap = 0;
     return P;
 }
 
@@ -240,6 +244,10 @@ int launch_step(fdlbm_engine *e, bool finalize)
             k_step_twopass<T, false><<<cell_grid(e, e->Wl), TPB, 0, e->stream>>>(P, field_ptrs<T>(e));
         e->launches += 2;
     } else {
+#if FDLBM_STEAL && !defined(FDLBM_STEAL_DRY)  // FDLBM_STEAL_DRY: the stealing build with its table switched off (A/B of the loop structure)
+        P.steal = e->steal_tab;
+        P.steal_cap = STEAL_CAP;
+#endif
         int rc = launch_fused_auto<T>(P, e->stream);
         if (rc) return fail(FDLBM_E_CUDA, "fused launch configuration failed (%d)", rc);
         e->launches += 1;
@@ -520,6 +528,10 @@ int fdlbm_create(const fdlbm_config *cfg, fdlbm_engine **out)
         CUE(cudaMalloc(&e->psi[k], e->plane_elems() * e->esize));
         CUE(cudaMemsetAsync(e->psi[k], 0, e->plane_elems() * e->esize, e->stream));
     }
+#if FDLBM_STEAL
+    CUE(cudaMalloc((void **)&e->steal_tab, 5 * STEAL_CAP * sizeof(int)));
+    CUE(cudaMemsetAsync(e->steal_tab, 0, 5 * STEAL_CAP * sizeof(int), e->stream));
+#endif
     CUE(cudaMalloc((void **)&e->flags, 256));
     CUE(cudaMemsetAsync(e->flags, 0, 256, e->stream));
     // the flag arrays carry one spare (zero) column: the step kernels load flags three columns ahead without a bound check
@@ -560,7 +572,7 @@ void fdlbm_destroy(fdlbm_engine *e)
             cudaIpcCloseMemHandle(e->peer_flags[side]);
         }
     void *ptrs[] = {e->lat[0], e->lat[1], e->psi[0], e->psi[1], e->fields, e->reflect, e->solid_bytes,
-                    e->solid, e->inlet, e->outlet, e->staging, e->flags};
+                    e->solid, e->inlet, e->outlet, e->staging, e->flags, e->steal_tab};
     for (void *p : ptrs)
         if (p) cudaFree(p);
     if (e->stream) cudaStreamDestroy(e->stream);

@@ -37,6 +37,9 @@ struct LbmParams {
     // two edge columns straight into their ghost columns (halo exchange fused into the step)
     T *peer_lo, *peer_hi;
     int peer_lo_Wl;           // owned columns of the low-side neighbour (its high ghosts are columns Wl, Wl+1)
+    // work table of the column-range stealing build (-DFDLBM_STEAL=1): {end, next column} per CTA, or nullptr
+    int *steal;
+    int steal_cap;            // CTAs the table has room for
 };
 
 // macroscopic outputs of the finalize pass / inputs of the first collision, each [(xl+G)*Hp + y]

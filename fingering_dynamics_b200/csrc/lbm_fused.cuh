@@ -134,6 +134,30 @@ __device__ __forceinline__ void mbar_wait(void *bar, unsigned parity)
         : "memory");
 }
 
+#ifndef FDLBM_STEAL
+#define FDLBM_STEAL 0  // 1: a CTA that has finished its column range takes over half of the slowest same-strip CTA's rest
+#endif
+#ifndef FDLBM_STEAL_MIN
+#define FDLBM_STEAL_MIN 12
+#endif
+constexpr int STEAL_MIN = FDLBM_STEAL_MIN;  // columns a range must still have for a steal to pay for its 3-column warm-up
+__device__ __forceinline__ int ld_vol(const int *p)
+{
+    int v;
+    asm volatile("ld.volatile.global.s32 %0, [%1];" : "=r"(v) : "l"(p));  // no memory clobber: a compiler barrier here
+                                                                          // serialises the f loads of the whole iteration
+    return v;
+}
+__device__ __forceinline__ void st_vol(int *p, int v) { asm volatile("st.volatile.global.s32 [%0], %1;" ::"l"(p), "r"(v)); }
+__device__ __forceinline__ void st_vol2(int *p, int a, int b)  // both words of a table entry at once
+{
+    asm volatile("st.volatile.global.v2.s32 [%0], {%1, %2};" ::"l"(p), "r"(a), "r"(b));
+}
+__device__ __forceinline__ void ld_vol2(const int *p, int &a, int &b)
+{
+    asm volatile("ld.volatile.global.v2.s32 {%0, %1}, [%2];" : "=r"(a), "=r"(b) : "l"(p));
+}
+
 template <typename T, int TY>
 struct FusedCfg {
     static constexpr int HALO = 16 / (int)sizeof(T);      // rows of apron per side: keeps 16-byte chunks aligned
@@ -218,8 +242,24 @@ __global__ void __launch_bounds__(TY, sizeof(T) == 8 ? FDLBM_FUSED_MINB64 : FDLB
     const int H = P.H, Hp = HPC > 0 ? HPC : P.Hp;
 
     const int yt = blockIdx.x % nyt;
+#if FDLBM_STEAL
+    int xs = (blockIdx.x / nyt) * chunk;  // the column range changes when this CTA takes over part of another's
+    int xe = min(P.Wl, xs + chunk);
+    // The end of my range travels table -> shared memory with the g stages' own cp.async groups (16 bytes, L2 path):
+    // a plain load kept in flight across the loop edge makes ptxas wait for it at the loop head.
+    __shared__ __align__(16) int s_end[2][4];
+    __shared__ int s_range[2];
+    const bool steal = P.steal != nullptr && (int)gridDim.x <= P.steal_cap;
+    // end markers: one 16-byte entry per CTA (what cp.async.cg moves); progress words live in their own region -- a
+    // progress store followed by the cp.async of the SAME entry cost 17 % (store -> load on one address), apart 2 % each
+    int *const my_tab = P.steal + 4 * blockIdx.x;                       // [0] = end of my range
+    int *const my_prog = P.steal + 4 * P.steal_cap + blockIdx.x;        // the column I am working on
+    unsigned par = 0;                              // phase parity of the NS stage barriers, one bit each
+    int fill_hi = 0, wait_hi = 0;                  // highest g column whose bulk fill was issued / waited for
+#else
     const int xs = (blockIdx.x / nyt) * chunk;
     const int xe = min(P.Wl, xs + chunk);
+#endif
     const int y0 = yt * TY;
     const int y = y0 + t;
     const int ny = min(TY, H - y0);
@@ -262,6 +302,9 @@ __global__ void __launch_bounds__(TY, sizeof(T) == 8 ? FDLBM_FUSED_MINB64 : FDLB
     auto prefetch = [&](int v) {
         const int cg = v + 2 + D;
         if (cg >= xs - 2 && cg <= xe + 1) {
+#if FDLBM_STEAL
+            fill_hi = cg;
+#endif
             T *stage = gst + slot(cg) * FAM;
             const T *col = P.src + lat_idx(Hp, cg, 9, 0);
             if (bulk) {
@@ -289,9 +332,20 @@ __global__ void __launch_bounds__(TY, sizeof(T) == 8 ? FDLBM_FUSED_MINB64 : FDLB
     };
     // wait until g column c has landed in its stage (bulk path: the fill of column c is the
     // ((c - (xs-2)) / NS)-th use of its mbarrier, whose parity is waited for)
+#if FDLBM_STEAL
+    auto landed = [&](int c) {  // every fill is waited for exactly once: the parity of a stage barrier is a running bit
+        if (bulk) {
+            const int s_ = slot(c);
+            mbar_wait(&bars[s_], (par >> s_) & 1u);
+            par ^= 1u << s_;
+            wait_hi = c;
+        }
+    };
+#else
     auto landed = [&](int c) {
         if (bulk) mbar_wait(&bars[slot(c)], (unsigned)(((c - (xs - 2)) / NS) & 1));
     };
+#endif
     // Per-cell flags are plain global loads issued two columns ahead of their use and carried RAW in
     // registers: nothing depends on them until they are decoded two iterations later, so their latency
     // never sits on the critical path.
@@ -339,6 +393,18 @@ __global__ void __launch_bounds__(TY, sizeof(T) == 8 ? FDLBM_FUSED_MINB64 : FDLB
     const RawFlags z{0u, 0u};
     RawFlags fq0 = z, fq1 = z, eq0 = z, eq1 = z;               // look-ahead queues: own / edge-neighbour cell, columns x+1, x+2
 
+#if FDLBM_STEAL
+    for (;;) {  // one pass per column range: the CTA's own, then the ones it takes over
+    if (steal && t == 0) {
+        st_vol(my_tab, 0);      // never (old end, new progress): that pair could look like columns left to take
+        __threadfence();
+        st_vol(my_prog, xs);
+        __threadfence();
+        st_vol(my_tab, xe);
+        s_end[xs & 1][0] = xe;  // what iteration xs reads (the warm-up below has barriers)
+    }
+    fill_hi = wait_hi = xs - 3;
+#endif
     // pipeline warm-up.  Steps v = xs-4-D .. xs-2 bring in g columns xs-2 .. xs+D (all NS slots);
     // psi(xs-1) needs g columns xs-2..xs, then g column xs-2 makes room for column xs+1+D.
     for (int v = xs - 4 - D; v < xs - 1; ++v) prefetch(v);
@@ -367,15 +433,36 @@ __global__ void __launch_bounds__(TY, sizeof(T) == 8 ? FDLBM_FUSED_MINB64 : FDLB
     psi_column(xs, fl_cur, decode(re_0, ye1), g_cur, p0_m, p0_0, p0_p);
 
     for (int x = xs; x < xe; ++x) {
+#if FDLBM_STEAL
+#ifndef FDLBM_STEAL_NOSTORE
+        if (steal && t == 0) st_vol(my_prog, x);  // my progress, for whoever looks for work
+#endif
+#endif
         cp_async_wait<D - 1>();  // g column x+2 has landed
         landed(x + 2);
         __syncthreads();         // ... for every thread; and everybody is done with iteration x-1
+#if FDLBM_STEAL
+        if (steal) {  // somebody took over the rest of this range from column s_end on (CTA-uniform)
+            const int en = s_end[x & 1][0];
+            if (en < xe) {
+                xe = en;
+                if (x >= xe) break;
+            }
+        }
+#endif
         // Decode the flags of column x+1 BEFORE any new global load is issued: they were loaded two iterations
         // ago, but the hardware scoreboard slots are shared -- decoding them after this iteration's f loads
         // would wait for those loads too (measured: 18 % of all stall samples on the first psi shuffle).
         fl_nxt = decode(fq0, y);
         unsigned fe_nxt = decode(eq0, ye1);
         asm volatile("" : "+r"(fl_nxt), "+r"(fe_nxt)::"memory");
+#if FDLBM_STEAL
+#ifndef FDLBM_STEAL_NOCP
+        if (steal && t == 0) cp_async16(&s_end[(x + 1) & 1][0], my_tab);  // lands with g column x+3, read after the next barrier
+#else
+        if (steal && t == 0) s_end[(x + 1) & 1][0] = xe;
+#endif
+#endif
         prefetch(x);             // overwrites the stage of g column x-1: no longer read
         T f[9];
         {
@@ -425,6 +512,50 @@ __global__ void __launch_bounds__(TY, sizeof(T) == 8 ? FDLBM_FUSED_MINB64 : FDLB
         eq0 = eq1, eq1 = eq2;
     }
     cp_async_wait<0>();
+#if FDLBM_STEAL
+    if (bulk)
+        for (int c = wait_hi + 1; c <= fill_hi; ++c) landed(c);  // fills issued before the range was cut short
+    if (!steal) break;
+    if (t == 0) st_vol(my_prog, 0x3fffffff);  // nothing left to take from me
+    __syncthreads();                             // everybody is done with the stages of this range
+    if (t < 32) {
+        // warp 0: the same-strip CTA with the most columns left hands over the second half of them.  Columns that
+        // end up processed twice (stale progress, races between thieves) are written with identical values.
+        const int nchunks = (int)gridDim.x / nyt;
+        int nxs = -1, nxe = -1;
+        for (int attempt = 0; attempt < 3 && nxs < 0; ++attempt) {
+            int brem = 0, bc = -1;
+            for (int c = lane; c < nchunks; c += 32) {
+                const int k2 = c * nyt + yt;
+                const int e_ = ld_vol(P.steal + 4 * k2), p_ = ld_vol(P.steal + 4 * P.steal_cap + k2);
+                if (e_ - p_ > brem) brem = e_ - p_, bc = c;
+            }
+#pragma unroll
+            for (int o = 16; o; o >>= 1) {
+                const int r2 = __shfl_xor_sync(FULL, brem, o), c2 = __shfl_xor_sync(FULL, bc, o);
+                if (r2 > brem || (r2 == brem && c2 > bc)) brem = r2, bc = c2;
+            }
+            if (brem < STEAL_MIN) break;
+            if (lane == 0) {
+                int *vt = P.steal + 4 * (bc * nyt + yt);
+                const int e_ = ld_vol(vt), p_ = ld_vol(P.steal + 4 * P.steal_cap + bc * nyt + yt);
+                if (e_ - p_ >= STEAL_MIN) {
+                    const int ne = p_ + 2 + (e_ - p_ - 1) / 2;  // the victim keeps the first half, two columns of slack
+                    // only if the victim still works on the range just read (it may have moved on to another one)
+                    if (atomicCAS(vt, e_, ne) == e_) nxs = ne, nxe = e_;
+                }
+            }
+            nxs = __shfl_sync(FULL, nxs, 0);
+            nxe = __shfl_sync(FULL, nxe, 0);
+        }
+        if (lane == 0) s_range[0] = nxs, s_range[1] = nxe;
+    }
+    __syncthreads();
+    xs = s_range[0];
+    xe = s_range[1];
+    if (xs < 0) break;
+    }  // for (;;) over column ranges
+#endif
     timer.stop(yt);
 }
 
