@@ -141,6 +141,16 @@ __device__ __forceinline__ void mbar_wait(void *bar, unsigned parity)
 #define FDLBM_STEAL_MIN 12
 #endif
 constexpr int STEAL_MIN = FDLBM_STEAL_MIN;  // columns a range must still have for a steal to pay for its 3-column warm-up
+#ifndef FDLBM_STEAL_EVERY
+#define FDLBM_STEAL_EVERY 1  // progress is published and the end marker fetched every so many columns (a power of two)
+#endif
+constexpr int STEAL_EVERY = FDLBM_STEAL_EVERY;
+static_assert(STEAL_EVERY > 0 && (STEAL_EVERY & (STEAL_EVERY - 1)) == 0, "FDLBM_STEAL_EVERY must be a power of two");
+// columns a victim may run past a lowered end marker: it reads the marker fetched one block of STEAL_EVERY columns ago,
+// and its published progress is up to STEAL_EVERY - 1 columns old
+constexpr int STEAL_SLACK = 3 * STEAL_EVERY - 1;
+static_assert(STEAL_MIN >= STEAL_SLACK + 8, "raise FDLBM_STEAL_MIN with FDLBM_STEAL_EVERY: a steal must leave both sides some columns");
+__device__ __forceinline__ int steal_block(int x) { return x / STEAL_EVERY; }  // x >= 0
 __device__ __forceinline__ int ld_vol(const int *p)
 {
     int v;
@@ -401,7 +411,7 @@ __global__ void __launch_bounds__(TY, sizeof(T) == 8 ? FDLBM_FUSED_MINB64 : FDLB
         st_vol(my_prog, xs);
         __threadfence();
         st_vol(my_tab, xe);
-        s_end[xs & 1][0] = xe;  // what iteration xs reads (the warm-up below has barriers)
+        s_end[0][0] = s_end[1][0] = xe;  // what the first iterations read (the warm-up below has barriers)
     }
     fill_hi = wait_hi = xs - 3;
 #endif
@@ -435,7 +445,7 @@ __global__ void __launch_bounds__(TY, sizeof(T) == 8 ? FDLBM_FUSED_MINB64 : FDLB
     for (int x = xs; x < xe; ++x) {
 #if FDLBM_STEAL
 #ifndef FDLBM_STEAL_NOSTORE
-        if (steal && t == 0) st_vol(my_prog, x);  // my progress, for whoever looks for work
+        if (steal && t == 0 && (x & (STEAL_EVERY - 1)) == 0) st_vol(my_prog, x);  // my progress, for whoever looks for work
 #endif
 #endif
         cp_async_wait<D - 1>();  // g column x+2 has landed
@@ -443,7 +453,7 @@ __global__ void __launch_bounds__(TY, sizeof(T) == 8 ? FDLBM_FUSED_MINB64 : FDLB
         __syncthreads();         // ... for every thread; and everybody is done with iteration x-1
 #if FDLBM_STEAL
         if (steal) {  // somebody took over the rest of this range from column s_end on (CTA-uniform)
-            const int en = s_end[x & 1][0];
+            const int en = s_end[steal_block(x) & 1][0];
             if (en < xe) {
                 xe = en;
                 if (x >= xe) break;
@@ -458,9 +468,10 @@ __global__ void __launch_bounds__(TY, sizeof(T) == 8 ? FDLBM_FUSED_MINB64 : FDLB
         asm volatile("" : "+r"(fl_nxt), "+r"(fe_nxt)::"memory");
 #if FDLBM_STEAL
 #ifndef FDLBM_STEAL_NOCP
-        if (steal && t == 0) cp_async16(&s_end[(x + 1) & 1][0], my_tab);  // lands with g column x+3, read after the next barrier
+        // lands with g column x+3; read from the first iteration of the next block on (the other slot is read until then)
+        if (steal && t == 0 && (x & (STEAL_EVERY - 1)) == 0) cp_async16(&s_end[(steal_block(x) + 1) & 1][0], my_tab);
 #else
-        if (steal && t == 0) s_end[(x + 1) & 1][0] = xe;
+        if (steal && t == 0 && (x & (STEAL_EVERY - 1)) == 0) s_end[(steal_block(x) + 1) & 1][0] = xe;
 #endif
 #endif
         prefetch(x);             // overwrites the stage of g column x-1: no longer read
@@ -540,7 +551,7 @@ __global__ void __launch_bounds__(TY, sizeof(T) == 8 ? FDLBM_FUSED_MINB64 : FDLB
                 int *vt = P.steal + 4 * (bc * nyt + yt);
                 const int e_ = ld_vol(vt), p_ = ld_vol(P.steal + 4 * P.steal_cap + bc * nyt + yt);
                 if (e_ - p_ >= STEAL_MIN) {
-                    const int ne = p_ + 2 + (e_ - p_ - 1) / 2;  // the victim keeps the first half, two columns of slack
+                    const int ne = p_ + STEAL_SLACK + (e_ - p_ - STEAL_SLACK + 1) / 2;  // the victim keeps the first half
                     // only if the victim still works on the range just read (it may have moved on to another one)
                     if (atomicCAS(vt, e_, ne) == e_) nxs = ne, nxe = e_;
                 }
