@@ -138,3 +138,25 @@ def test_validation_random_cases(mg, seed):
         _compare(run.iterate(steps), want, None, (H, W, pw, steps))
     finally:
         VA.H, VA.W, VA.psi_wall = old
+
+
+def test_validation_shipped_size_full_run_bit_exact(mg, golden):
+    """config 2 as shipped (validation.py: 200x250, psi_wall = 0, MAX_T = 1000): the oracle, started from the reference's
+    own Compute() state, against the reference's sums and subsampled fields at iterations 10, 100, 500, 1000."""
+    VA = mg.VA
+    d = dict(golden("va_full_scalars"))
+    assert (VA.H, VA.W, VA.psi_wall) == (int(d["H"]), int(d["W"]), float(d["c_psi_wall"]))
+    with _quiet():
+        cm = VA.Compute()
+    d["e"], d["w"] = cm.e.copy(), cm.w.copy()
+    mg.snap_va(cm, "s0", d)
+    run = hp.va_run(d)
+    done = 0
+    for step in (10, 100, 500, 1000):
+        a = run.iterate(step - done)
+        done = step
+        tag = "s%d" % step
+        assert a["psi"].sum() == float(d[tag + "_sum_psi"]), step
+        assert a["rho"].sum() == float(d[tag + "_sum_rho"]), step
+        for k in ("psi", "rho", "ux", "uy"):
+            assert np.array_equal(a[k][::5, ::5], d["%s_%s_sub" % (tag, k)]), (step, k)
