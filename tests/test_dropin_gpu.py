@@ -174,3 +174,32 @@ def test_validation_shipped_configuration_against_reference_scalars(golden):
         for k in ("psi", "rho", "ux", "uy"):
             assert hp.rel_err(st[k][::5, ::5], d["%s_%s_sub" % (tag, k)]) <= TOL, (step, k)
     eng.close()
+
+
+def test_fingering_periodic_gpu_twin_against_the_oracle():
+    """The CuPy variant of the reference cannot run anywhere without CuPy, so its twin is checked
+    against the oracle: same constants (fingering_periodic_gpu.py:20-45), the twin's initial state, uniform Zou-He
+    faces with the 2/3 coefficient, no obstacles; 25 iterations on the shipped 400x420 grid."""
+    from oracle import oracle as orc
+    from fingering_dynamics_b200 import geometry as geo
+    from fingering_dynamics_b200.lattice_boltzmann import fingering_periodic_gpu as G, _compute
+    H, W = G.H, G.W
+    np.random.seed(3)
+    mask = np.ones((H, W), dtype=bool)
+    cm = G.Compute(mask)
+    assert (cm.psi[:, :10] == 1.0).all() and (cm.psi[:, 10:] == -1.0).all() and not cm.mu.any()
+    assert 0.95 <= cm.rho.min() and cm.rho.max() <= 1.0 and cm.rho.std() > 0.01
+    s0 = dict(f=cm.f.copy(), g=cm.g.copy(), psi=cm.psi.copy(), rho=cm._full(cm.rho), ux=cm._full(cm.ux),
+              uy=cm._full(cm.uy), p=cm._full(cm.p), mu=cm._full(cm.mu), mix_tau=cm._full(cm.mix_tau),
+              gx=cm.nabla_psix.copy(), gy=cm.nabla_psiy.copy(), lap=cm.nabla_psi2.copy())
+    P = orc.make_params(H, W, tau=G.tau, gamma=G.gamma, a=G.a, kappa=G.kappa, Eta_n=G.Eta_n, M=G.M, psi_wall=G.psi_wall,
+                        y_wall=0, outlet_f3_coef=2 / 3)
+    u = np.full(H, float(G.u0))
+    run = orc.Run(P, s0, mask=mask, circ_masks=np.zeros((12, H, W), dtype=np.uint8), zou_he=1, inlet_ux=u, outlet_ux=u)
+    want = run.iterate(25)
+    frames = _compute.run_loop(cm, geo.reflect_bits_circle([~mask] * 4, [~mask] * 4, [~mask] * 4), 25, frames_every=10)
+    assert len(frames) == 3 and np.array_equal(frames[0], s0["psi"])
+    assert hp.rel_err(cm.psi, want["psi"]) <= TOL
+    for k in ("rho", "ux", "uy", "p", "mu"):
+        assert hp.rel_err(cm._full(getattr(cm, k)), np.where(mask, want[k], 0.0)) <= TOL, k
+    assert hp.rel_err(cm.f, want["f"]) <= TOL and hp.rel_err(cm.g, want["g"]) <= TOL
