@@ -115,6 +115,14 @@ def reflect_bits(corner_list):
     return _geo.reflect_bits_rect(corner_list, H, W) | _geo.reflect_bits_wall_rows(H, W, 1, H - 2)
 
 
+def update(i, x, y, cc):
+    """animation callback of the reference (fingering.py:422-425): draw psi frame i of cc"""
+    print(i)
+    import matplotlib.pyplot as plt
+    plt.cla()
+    plt.pcolor(x, y, cc[i], label='MAX_T{}_Pe{}_M{}_Ca{}_wall{}'.format(MAX_T, Pe, M, Ca, psi_wall), cmap='RdBu')
+
+
 def main(max_t=None, show=True):
     cr = Createblock(H, W)
     Bounce_back(H, W)

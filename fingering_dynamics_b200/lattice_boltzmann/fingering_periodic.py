@@ -101,6 +101,14 @@ def default_circles():
     return circle_list
 
 
+def update(i, x, y, cc):
+    """animation callback of the reference (fingering_periodic.py:346-349): draw psi frame i of cc"""
+    print(i)
+    import matplotlib.pyplot as plt
+    plt.cla()
+    plt.pcolor(x, y, cc[i], label='MAX_T{}_Pe{}_M{}_Ca{}_wall{}'.format(MAX_T, Pe, M, Ca, psi_wall), cmap='RdBu')
+
+
 def main(max_t=None, show=True):
     cr = Createblock(H, W)
     Bounce_back(H, W)

@@ -91,6 +91,14 @@ def stream(f, g):
     _stream(f, g)
 
 
+def update(i, x, y, cc):
+    """animation callback of the reference (fingering_periodic_gpu.py, same as fingering_periodic.py:346-349): draw psi frame i of cc"""
+    print(i)
+    import matplotlib.pyplot as plt
+    plt.cla()
+    plt.pcolor(x, y, cc[i], label='MAX_T{}_Pe{}_M{}_Ca{}_wall{}'.format(MAX_T, Pe, M, Ca, psi_wall), cmap='RdBu')
+
+
 def main(max_t=None, show=False):
     """fingering_periodic_gpu.py:446-560: no obstacles (:473), psi frames every MAX_T // 150 iterations (:479,527).
     Returns cm with the frames in cm.frames (as the fingering.py twin does)."""

@@ -82,6 +82,9 @@ class Compute(ComputeBase):
         self.feq, self.geq = feq, geq
         self.f, self.g = feq.copy(), geq.copy()
 
+    def power_law(self, temp2):
+        return power_law(self, temp2)
+
     def updateP(self):
         self.p = self.getP()
 
@@ -109,6 +112,56 @@ def stream(f, g):
 
 def halfway_bounceback(f_behind, g_behind, f, g):
     _wall_rows(f_behind, g_behind, f, g)
+
+
+def update(i, x, y, cc):
+    """animation callback of the reference (validation.py:379-384): draw psi frame i of cc"""
+    print(i)
+    import matplotlib.pyplot as plt
+    plt.cla()
+    plt.pcolor(x, y, cc[i], label="MAX_T:{}, Pe:{}, M:{}, wall{}".format(MAX_T, Pe, M, psi_wall))
+    plt.legend()
+
+
+# validation.py:193 ends `class Compute` early: the functions below are MODULE-level there (taking `self`), and callers
+# bind them back onto the class.  Same names here, forwarding to the methods.
+x_array = np.arange(0.1, 1.0, 0.01)  # validation.py:40
+
+
+def power_law(self, temp2):
+    """validation.py:219-225 (unused non-Newtonian relaxation time: nearest-neighbour inverse of
+    x - temp2 x^(1-n) - dt/2 on x_array)"""
+    from scipy import interpolate
+    y_array = x_array - temp2 * x_array ** (1 - n_non) - 0.5 * DELTA_T
+    return interpolate.interp1d(y_array.real, x_array, kind='nearest', fill_value='extrapolate')(0)
+
+
+def getMix_tau(self):
+    return Compute.getMix_tau(self)
+
+
+def updatePsi(self):
+    return Compute.updatePsi(self)
+
+
+def getNabla_psix(self):
+    return Compute.getNabla_psix(self)
+
+
+def getNabla_psiy(self):
+    return Compute.getNabla_psiy(self)
+
+
+def getNabla_psi2(self):
+    return Compute.getNabla_psi2(self)
+
+
+def updateF(self):
+    return Compute.updateF(self)
+
+
+def updateG(self):
+    return Compute.updateG(self)
 
 
 def main(max_t=None, show=True):

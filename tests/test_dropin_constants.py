@@ -67,3 +67,22 @@ def test_createblock_and_bounce_back_surface(mg):
         rc, tc = getattr(ref, cls), getattr(twin, cls)
         for m in [k for k, v in vars(rc).items() if callable(v) and not k.startswith("_")]:
             assert callable(getattr(tc, m, None)), "%s.%s is missing in the twin" % (cls, m)
+
+
+@pytest.mark.parametrize("name", ["fingering_periodic", "fingering", "validation"])
+def test_functions_and_compute_methods_of_the_reference_exist_in_the_twin(mg, name):
+    import inspect
+    ref = {"fingering_periodic": mg.FP, "fingering": mg.FG, "validation": mg.VA}[name]
+    twin = importlib.import_module("fingering_dynamics_b200.lattice_boltzmann." + name)
+    ref_methods = {k for k, v in vars(ref.Compute).items() if callable(v) and not k.startswith("__")}
+    twin_methods = {k for k in dir(twin.Compute) if callable(getattr(twin.Compute, k))}
+    assert not (ref_methods - twin_methods), sorted(ref_methods - twin_methods)
+    ref_funcs = {k for k, v in vars(ref).items() if inspect.isfunction(v) and v.__module__ == ref.__name__}
+    twin_funcs = {k for k, v in vars(twin).items() if callable(v)}
+    assert not (ref_funcs - twin_funcs), sorted(ref_funcs - twin_funcs)
+
+
+def test_validation_power_law_matches_the_reference(mg):
+    from fingering_dynamics_b200.lattice_boltzmann import validation as V
+    for t in (0.0, 0.05, 0.2, 0.37):
+        assert float(V.power_law(None, t)) == float(mg.VA.power_law(None, t))
