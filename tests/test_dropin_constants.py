@@ -86,3 +86,30 @@ def test_validation_power_law_matches_the_reference(mg):
     from fingering_dynamics_b200.lattice_boltzmann import validation as V
     for t in (0.0, 0.05, 0.2, 0.37):
         assert float(V.power_law(None, t)) == float(mg.VA.power_law(None, t))
+
+
+def _required(f):
+    import inspect
+    return [p.name for p in inspect.signature(f).parameters.values()
+            if p.default is inspect._empty and p.kind in (p.POSITIONAL_ONLY, p.POSITIONAL_OR_KEYWORD)]
+
+
+@pytest.mark.parametrize("name", ["fingering_periodic", "fingering", "validation", "create_block", "bounce_back"])
+def test_required_arguments_equal_the_reference(mg, name):
+    """same positional arguments, by name and order, for every function and method both modules define"""
+    import inspect
+    ref = {"fingering_periodic": mg.FP, "fingering": mg.FG, "validation": mg.VA, "create_block": mg.CB,
+           "bounce_back": mg.BB}[name]
+    twin = importlib.import_module("fingering_dynamics_b200.lattice_boltzmann." + name)
+    checked = 0
+    for cname in ("Compute", "Createblock", "Bounce_back"):
+        if hasattr(ref, cname):
+            for k, v in vars(getattr(ref, cname)).items():
+                if callable(v) and hasattr(getattr(twin, cname), k):
+                    assert _required(v) == _required(getattr(getattr(twin, cname), k)), (cname, k)
+                    checked += 1
+    for k, v in vars(ref).items():
+        if inspect.isfunction(v) and v.__module__ == ref.__name__ and hasattr(twin, k):
+            assert _required(v) == _required(getattr(twin, k)), k
+            checked += 1
+    assert checked >= 4
