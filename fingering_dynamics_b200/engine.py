@@ -145,10 +145,13 @@ class Engine:
         nat.check(nat.lib().fdlbm_checkpoint_load(self._h, nat.ptr(buf), buf.size))
 
     def save(self, path):
-        np.save(path, self.checkpoint(), allow_pickle=False)
+        """checkpoint() to exactly `path` (np.save on a file name would append '.npy')"""
+        with open(path, "wb") as fh:
+            np.save(fh, self.checkpoint(), allow_pickle=False)
 
     def load(self, path):
-        self.restore(np.load(path, allow_pickle=False))
+        with open(path, "rb") as fh:
+            self.restore(np.load(fh, allow_pickle=False))
 
     def count_nonfinite(self):
         n = ctypes.c_int64(0)

@@ -224,3 +224,20 @@ def test_ctypes_structures_match_the_header_layout(tmp_path):
         cls = pairs[name]
         assert ctypes.sizeof(cls) == int(size), name
         assert [getattr(cls, f[0]).offset for f in cls._fields_] == [int(o) for o in offs], name
+
+
+def test_engine_save_and_load_use_the_exact_path(tmp_path):
+    """Engine.save / Engine.load around checkpoint() / restore(), without a device: the blob round-trips through the
+    file name given (no '.npy' appended)."""
+    from fingering_dynamics_b200 import Engine
+    e = object.__new__(Engine)
+    e._h = None
+    blob = np.arange(1000, dtype=np.uint8)
+    got = {}
+    e.checkpoint = lambda: blob
+    e.restore = lambda b: got.setdefault("blob", np.array(b))
+    path = tmp_path / "run.ckpt"
+    e.save(str(path))
+    assert path.exists() and not (tmp_path / "run.ckpt.npy").exists()
+    e.load(str(path))
+    assert np.array_equal(got["blob"], blob) and got["blob"].dtype == np.uint8
