@@ -4,6 +4,7 @@ There is no CPU path: if the library cannot be loaded, or no CUDA device is visi
 is created, the call raises.
 """
 import ctypes
+import hashlib
 import os
 import subprocess
 
@@ -12,32 +13,65 @@ import numpy as np
 _HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(_HERE, "csrc")
 LIB_PATH = os.path.join(CSRC, "libfdlbm.so")
-SOURCES = ["fdlbm.cu", "lbm_device.cuh", "lbm_kernels.cuh", "lbm_fused.cuh", "lbm_fused_vec.cuh", "lbm_fused_f32.cuh", "lbm_ops.cuh"]
+SOURCES = ["fdlbm.cu", "lbm_device.cuh", "lbm_kernels.cuh", "lbm_fused.cuh", "lbm_fused_vec.cuh", "lbm_fused_f32.cuh", "lbm_ops.cuh", "lbm_init.cuh"]
 HEADER = os.path.join(os.path.dirname(_HERE), "include", "fdlbm.h")
 
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17", "--shared",
               "-Xcompiler", "-fPIC"]
 
 
+STAMP_PATH = LIB_PATH + ".srchash"
+
+
+def _source_hash():
+    """sha256 over the sources, the header and the flags: what the library was built from (mtimes do not survive
+    a checkout or the copy to the GPU box)"""
+    h = hashlib.sha256(" ".join(NVCC_FLAGS).encode())
+    for d in [os.path.join(CSRC, s) for s in SOURCES] + [HEADER]:
+        h.update(b"\0" + os.path.basename(d).encode() + b"\0")
+        with open(d, "rb") as fh:
+            h.update(fh.read())
+    return h.hexdigest()
+
+
 def _stale():
     if not os.path.exists(LIB_PATH):
         return True
-    t = os.path.getmtime(LIB_PATH)
-    deps = [os.path.join(CSRC, s) for s in SOURCES] + [HEADER]
-    return any(os.path.exists(d) and os.path.getmtime(d) > t for d in deps)
+    try:
+        with open(STAMP_PATH) as fh:
+            return fh.read().strip() != _source_hash()
+    except OSError:
+        return True
 
 
 def build(force=False, verbose=False):
-    """nvcc-compile the CUDA library for sm_100a, in tree (cross-compiles without a GPU)."""
+    """nvcc-compile the CUDA library for sm_100a, in tree (cross-compiles without a GPU).  Safe under torchrun:
+    one process compiles (file lock) into a temporary file that is renamed into place, so no rank ever dlopens
+    a half-written library."""
     if not force and not _stale():
         return LIB_PATH
-    nvcc = os.environ.get("NVCC", "nvcc")
-    cmd = [nvcc] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-o", LIB_PATH, os.path.join(CSRC, "fdlbm.cu")]
-    r = subprocess.run(cmd, capture_output=True, text=True)
-    if r.returncode != 0:
-        raise RuntimeError("nvcc failed:\n" + r.stderr)
-    if verbose:
-        print(r.stderr)
+    import fcntl
+    with open(LIB_PATH + ".lock", "w") as lock:
+        fcntl.flock(lock, fcntl.LOCK_EX)
+        try:
+            if not force and not _stale():   # another process built it while we waited
+                return LIB_PATH
+            nvcc = os.environ.get("NVCC", "nvcc")
+            tmp = "%s.tmp.%d" % (LIB_PATH, os.getpid())
+            cmd = [nvcc] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-o", tmp, os.path.join(CSRC, "fdlbm.cu")]
+            r = subprocess.run(cmd, capture_output=True, text=True)
+            if r.returncode != 0:
+                if os.path.exists(tmp):
+                    os.unlink(tmp)
+                raise RuntimeError("nvcc failed:\n" + r.stderr)
+            if verbose:
+                print(r.stderr)
+            os.replace(tmp, LIB_PATH)
+            with open(STAMP_PATH + ".tmp", "w") as fh:
+                fh.write(_source_hash())
+            os.replace(STAMP_PATH + ".tmp", STAMP_PATH)
+        finally:
+            fcntl.flock(lock, fcntl.LOCK_UN)
     return LIB_PATH
 
 
@@ -60,6 +94,13 @@ FIELD_NAMES = ("f", "g", "psi", "rho", "ux", "uy", "p", "mu", "mix_tau", "nabla_
 class Fields(ctypes.Structure):
     """fdlbm_fields of include/fdlbm.h"""
     _fields_ = [(n, ctypes.c_void_p) for n in FIELD_NAMES]
+
+
+class Init(ctypes.Structure):
+    """fdlbm_init of include/fdlbm.h"""
+    _fields_ = [("variant", ctypes.c_int32), ("n_inject", ctypes.c_int32), ("psi_inject", ctypes.c_double),
+                ("psi_rest", ctypes.c_double), ("rho0", ctypes.c_double), ("rho", ctypes.c_void_p),
+                ("col0", ctypes.c_int32), ("ncols", ctypes.c_int32)]
 
 
 class Halo(ctypes.Structure):
@@ -88,6 +129,7 @@ _SIGS = {
     "fdlbm_destroy": (None, [ctypes.c_void_p]),
     "fdlbm_set_geometry": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int, ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p]),
     "fdlbm_set_state": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int, ctypes.c_int, ctypes.POINTER(Fields)]),
+    "fdlbm_init_state": (ctypes.c_int, [ctypes.c_void_p, ctypes.POINTER(Init)]),
     "fdlbm_step": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int]),
     "fdlbm_get_state": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int, ctypes.c_int, ctypes.POINTER(Fields)]),
     "fdlbm_iterations": (ctypes.c_int64, [ctypes.c_void_p]),

@@ -12,6 +12,7 @@
 #include "lbm_kernels.cuh"
 #include "lbm_fused.cuh"
 #include "lbm_fused_vec.cuh"
+#include "lbm_init.cuh"
 
 using namespace fdlbm;
 
@@ -456,6 +457,36 @@ int upload_profile(fdlbm_engine *e, const double *host, void **dev)
     return 0;
 }
 
+template <typename T>
+int init_state_t(fdlbm_engine *e, const fdlbm_init *spec)
+{
+    const fdlbm_config &c = e->cfg;
+    int rc = ensure_fields(e);
+    if (rc) return rc;
+    e->cur = 0;
+    e->pcur = 0;
+    CU(cudaMemsetAsync(e->lat[0], 0, e->lat_elems() * e->esize, e->stream));
+    CU(cudaMemsetAsync(e->lat[1], 0, e->lat_elems() * e->esize, e->stream));
+    CU(cudaMemsetAsync(e->fields, 0, 9 * e->plane_elems() * e->esize, e->stream));
+    if (spec->rho && (rc = upload_planes<T>(e, spec->rho, 1, spec->col0, spec->ncols, (T *)e->fields, 0, (size_t)e->Hp)))
+        return rc;
+    InitParams I{};
+    I.variant = spec->variant;
+    I.n_inject = spec->n_inject;
+    I.have_rho = spec->rho != nullptr;
+    I.psi_inject = spec->psi_inject, I.psi_rest = spec->psi_rest, I.rho0 = spec->rho0;
+    I.gamma = c.gamma, I.a = c.a, I.kappa = c.kappa, I.Eta_n = c.Eta_n, I.M = c.M;
+    I.psi_wall = c.psi_wall, I.psi_left = c.psi_left, I.psi_right = c.psi_right;
+    LbmParams<T> P = make_params<T>(e, 1, 0);  // dst = lat[0]
+    k_init_psi<T><<<cell_grid(e, e->ncols), TPB, 0, e->stream>>>(P, I, (T *)e->psi[0]);
+    k_init_cells<T><<<cell_grid(e, e->Wl), TPB, 0, e->stream>>>(P, I, field_ptrs<T>(e));
+    CU(cudaGetLastError());
+    e->launches += 2;
+    e->state = ST_PRE;
+    e->iters = 0;
+    return drain_transfers(e);
+}
+
 }  // namespace
 
 extern "C" {
@@ -588,6 +619,16 @@ int fdlbm_set_geometry(fdlbm_engine *e, int col0, int ncols, const uint8_t *soli
 {
     if (!e || !solid || !reflect) return fail(FDLBM_E_ARG, "null argument");
     if (ncols <= 0 || col0 < 0 || col0 + ncols > e->cfg.W) return fail(FDLBM_E_ARG, "bad column window");
+    // one call carries the whole geometry (the planes are rebuilt from scratch below): every local column that
+    // exists in the grid, ghosts included, must be inside the window
+    for (int xl = -G; xl < e->Wl + G; ++xl) {
+        int gx = e->cfg.x0 + xl;
+        if (e->cfg.x_periodic) gx = ((gx % e->cfg.W) + e->cfg.W) % e->cfg.W;
+        if (gx < 0 || gx >= e->cfg.W) continue;
+        if (gx < col0 || gx >= col0 + ncols)
+            return fail(FDLBM_E_ARG, "geometry window [%d,%d) does not cover column %d of the slab [%d,%d) and its ghost columns",
+                        col0, col0 + ncols, gx, e->cfg.x0, e->cfg.x1);
+    }
     CU(cudaSetDevice(e->cfg.device));
     const int H = e->cfg.H;
     const size_t bytes = (size_t)H * ncols;
@@ -620,9 +661,25 @@ int fdlbm_set_state(fdlbm_engine *e, int col0, int ncols, const fdlbm_fields *in
         !in->nabla_psix || !in->nabla_psiy)
         return fail(FDLBM_E_ARG, "set_state needs f, g, psi, rho, ux, uy, p, mu, mix_tau, nabla_psix, nabla_psiy");
     if (ncols <= 0 || col0 < 0 || col0 + ncols > e->cfg.W) return fail(FDLBM_E_ARG, "bad column window");
+    if (col0 > e->cfg.x0 || col0 + ncols < e->cfg.x1)  // both lattices are cleared below: a partial window would lose the rest
+        return fail(FDLBM_E_ARG, "state window [%d,%d) does not cover the slab [%d,%d)", col0, col0 + ncols, e->cfg.x0, e->cfg.x1);
     if (!e->have_geometry) return fail(FDLBM_E_STATE, "set_geometry must be called before set_state");
     CU(cudaSetDevice(e->cfg.device));
     return e->cfg.dtype == FDLBM_F64 ? set_state_t<double>(e, col0, ncols, in) : set_state_t<float>(e, col0, ncols, in);
+}
+
+int fdlbm_init_state(fdlbm_engine *e, const fdlbm_init *spec)
+{
+    if (!e || !spec) return fail(FDLBM_E_ARG, "null argument");
+    if (spec->variant != FDLBM_INIT_FP && spec->variant != FDLBM_INIT_FG) return fail(FDLBM_E_ARG, "bad init variant %d", spec->variant);
+    if (spec->n_inject < 0) return fail(FDLBM_E_ARG, "negative n_inject");
+    if (!spec->rho && !(spec->rho0 > 0)) return fail(FDLBM_E_ARG, "rho0 must be positive");
+    if (spec->rho && (spec->ncols <= 0 || spec->col0 > e->cfg.x0 || spec->col0 + spec->ncols < e->cfg.x1))
+        return fail(FDLBM_E_ARG, "the rho window [%d,%d) does not cover the slab [%d,%d)", spec->col0, spec->col0 + spec->ncols,
+                    e->cfg.x0, e->cfg.x1);
+    if (!e->have_geometry) return fail(FDLBM_E_STATE, "set_geometry must be called before init_state");
+    CU(cudaSetDevice(e->cfg.device));
+    return e->cfg.dtype == FDLBM_F64 ? init_state_t<double>(e, spec) : init_state_t<float>(e, spec);
 }
 
 int fdlbm_step(fdlbm_engine *e, int n)
@@ -700,6 +757,9 @@ int fdlbm_checkpoint_save(fdlbm_engine *e, void *host, size_t bytes)
     char *p = (char *)host;
     memcpy(p, &h, sizeof h);
     p += sizeof h;
+    // the ghost columns of lat[cur] are written by the attached neighbours' step kernels: wait for their step
+    // `peer_step` like get_state does (all ranks of a slab run checkpoint / restore at the same step)
+    if (e->peer_mode() && (rc = peer_wait(e, e->peer_step))) return rc;
     CU(cudaStreamSynchronize(e->stream));
     CU(cudaMemcpy(p, e->lat[e->cur], e->lat_elems() * e->esize, cudaMemcpyDeviceToHost));
     p += e->lat_elems() * e->esize;
@@ -720,6 +780,7 @@ int fdlbm_checkpoint_load(fdlbm_engine *e, const void *host, size_t bytes)
     if (h.H != e->cfg.H || h.W != e->cfg.W || h.x0 != e->cfg.x0 || h.x1 != e->cfg.x1 || h.dtype != e->cfg.dtype ||
         h.Hp != e->Hp || h.ncols != e->ncols)
         return fail(FDLBM_E_ARG, "checkpoint was taken from a different grid / slab / dtype");
+    if (h.state != ST_PRE && h.state != ST_POST) return fail(FDLBM_E_ARG, "checkpoint blob holds no state (%d)", h.state);
     CU(cudaSetDevice(e->cfg.device));
     int rc = ensure_fields(e);
     if (rc) return rc;

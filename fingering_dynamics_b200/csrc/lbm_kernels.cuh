@@ -89,7 +89,11 @@ __global__ void __launch_bounds__(TPB) k_collide_first(const __grid_constant__ L
     int y, xl;
     block_cell(P.H, y, xl);
     if (y >= P.H) return;
-    if (is_solid(P, xl, y)) return;
+    // Solid cells are never collided, but what has streamed INTO them is part of the state (a restart from a
+    // step-k get_state has non-zero populations there): on the two edge columns of a peer-attached slab they must
+    // still reach the neighbour's ghost columns, unchanged.
+    const bool solid = is_solid(P, xl, y);
+    if (solid && !((P.peer_lo && xl < G) || (P.peer_hi && xl >= P.Wl - G))) return;
     const size_t c = cell_idx(P.Hp, xl, y);
     T f[9], g[9];
     const T *s = P.dst + lat_idx(P.Hp, xl, 0, y);
@@ -97,6 +101,10 @@ __global__ void __launch_bounds__(TPB) k_collide_first(const __grid_constant__ L
     for (int i = 0; i < 9; ++i) {
         f[i] = s[(size_t)i * P.Hp];
         g[i] = s[(size_t)(9 + i) * P.Hp];
+    }
+    if (solid) {
+        store_cell(P, xl, y, f, g);
+        return;
     }
     Macro<T> m;
     m.rho = in.rho[c];

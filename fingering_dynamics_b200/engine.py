@@ -79,7 +79,9 @@ class Engine:
 
     def set_geometry(self, solid, reflect, col0=0):
         """solid: (H,ncols) nonzero = block cell; reflect: (H,ncols) uint8 bits (see geometry.py)."""
-        s = np.ascontiguousarray(np.asarray(solid) != 0, dtype=np.uint8)
+        s = np.asarray(solid)
+        if not (s.dtype == np.uint8 and s.flags.c_contiguous):   # uint8 planes go up as they are (page-locked ones too):
+            s = np.ascontiguousarray(s != 0, dtype=np.uint8)      # the device packs "nonzero" into the bitfield
         r = np.ascontiguousarray(reflect, dtype=np.uint8)
         if s.shape != r.shape:
             raise ValueError("solid and reflect shapes differ")
@@ -110,6 +112,22 @@ class Engine:
             keep[k] = a
             setattr(F, k, a.ctypes.data)
         nat.check(nat.lib().fdlbm_set_state(self._h, int(col0), nc, ctypes.byref(F)))
+
+    def init_state(self, variant="fp", n_inject=5, psi_inject=1.0, psi_rest=-1.0, rho0=1.0, rho=None, col0=0):
+        """Compute.__init__ on the device (fingering_periodic.py:90-121 / fingering.py:95-127): no host planes
+        except an optional (H,ncols) `rho` (fingering.py draws it at random).  Leaves the engine where
+        set_state would; fp64 engines hold the reference's bits."""
+        spec = nat.Init()
+        spec.variant = {"fp": 1, "fg": 2}[variant]
+        spec.n_inject = int(n_inject)
+        spec.psi_inject, spec.psi_rest, spec.rho0 = float(psi_inject), float(psi_rest), float(rho0)
+        keep = None
+        if rho is not None:
+            keep = nat.as_f64(rho)
+            _, spec.ncols = self._window(keep.shape, col0)
+            spec.col0 = int(col0)
+            spec.rho = keep.ctypes.data
+        nat.check(nat.lib().fdlbm_init_state(self._h, ctypes.byref(spec)))
 
     # -- run ----------------------------------------------------------------------------------
     def step(self, n=1):

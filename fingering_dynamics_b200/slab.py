@@ -62,11 +62,39 @@ class SlabRunner:
     def set_state(self, **kw):
         """engine.set_state on every rank, then a barrier: a neighbour's first step writes into this rank's
         ghost columns, which must not happen before this rank has finished loading its state"""
+        self._before_load()
         self.e.set_state(**kw)
+        self._after_load()
+
+    def _before_load(self):
+        """nobody may still be stepping (pushing halo columns) into the lattices a load is about to overwrite"""
         if self.world > 1:
             import torch.distributed as dist
             self.e.sync()
             dist.barrier()
+
+    def _after_load(self):
+        if self.world > 1:
+            import torch.distributed as dist
+            self.e.sync()
+            dist.barrier()
+
+    def init_state(self, **kw):
+        """engine.init_state (Compute.__init__ on the device) on every rank, then the same barrier as set_state"""
+        self._before_load()
+        self.e.init_state(**kw)
+        self._after_load()
+
+    def checkpoint(self):
+        """every rank saves at the same step (the engine waits for its neighbours' halo stores of that step)"""
+        return self.e.checkpoint()
+
+    def restore(self, blob):
+        """every rank restores a blob of the same step; the barrier keeps a neighbour's first halo stores out of a
+        lattice that is still being loaded"""
+        self._before_load()
+        self.e.restore(blob)
+        self._after_load()
 
     # -- halo buffers ------------------------------------------------------------------------------
     def _tensors(self):

@@ -89,14 +89,38 @@ void fdlbm_destroy(fdlbm_engine *e);
 /* Geometry.  solid: 1 = block cell (block_psi_all == 1, fingering_periodic.py:450-451).
  * reflect: bit (i-1) set <=> after streaming, f_i and g_i of this cell are replaced by the pre-stream
  * f_opp(i), g_opp(i) of the SAME cell -- the union of the class tables of bounce_back.py:89-167 /
- * 25-86 and of the wall rows (fingering.py:573, validation.py:357-376).  Both (H,ncols) uint8. */
+ * 25-86 and of the wall rows (fingering.py:573, validation.py:357-376).  Both (H,ncols) uint8.
+ * ONE call carries the whole geometry of the engine: the window [col0, col0+ncols) must cover the slab AND its two
+ * ghost columns per side where those lie inside the grid (wrapped around for x-periodic grids), i.e.
+ * [max(0,x0-2), min(W,x1+2)) at least; earlier geometry is discarded.  FDLBM_E_ARG otherwise. */
 int fdlbm_set_geometry(fdlbm_engine *e, int col0, int ncols, const uint8_t *solid, const uint8_t *reflect);
 
 /* Load the state a reference iteration starts from: populations f,g plus the macroscopic arrays the
  * FIRST collision reads (rho, ux, uy, p, mu, mix_tau, psi, nabla_psix, nabla_psiy) exactly as the
  * caller holds them -- Compute.__init__ leaves them mutually inconsistent (fingering_periodic.py:111,
- * fingering.py:121-123) and parity needs that.  Resets the step counter. */
+ * fingering.py:121-123) and parity needs that.  Resets the step counter and discards the previous state: the
+ * window [col0, col0+ncols) must cover the slab [x0,x1) (FDLBM_E_ARG otherwise); ghost columns are not taken
+ * from it (they come from the halo exchange / local wrap). */
 int fdlbm_set_state(fdlbm_engine *e, int col0, int ncols, const fdlbm_fields *in);
+
+/* Compute.__init__ ON THE DEVICE (fingering_periodic.py:90-121, fingering.py:95-127) -- the alternative to
+ * fdlbm_set_state for grids whose 29 host planes would be the job's dominant transfer: psi = psi_inject on the
+ * first n_inject GLOBAL columns and psi_rest elsewhere (psi_wall on solids), rho = rho0 (or the caller's plane:
+ * fingering.py:106-107 draws it at random), u, mu, p, tau_mix, grad psi and f = f_eq, g = g_eq in the reference's
+ * operation order with the quirks parity depends on (FP: mu is still 0 everywhere, fingering_periodic.py:111;
+ * FG: p before mu, uy from mu but not ux, fingering.py:121-123).  fp64 engines get the reference's bits.
+ * Leaves the engine where fdlbm_set_state would (first collision from these arrays); resets the step counter. */
+enum { FDLBM_INIT_FP = 1, FDLBM_INIT_FG = 2 };
+typedef struct {
+    int32_t variant;              /* FDLBM_INIT_*                                                    */
+    int32_t n_inject;             /* 5 in both drivers (fingering_periodic.py:91, fingering.py:96)   */
+    double psi_inject, psi_rest;  /* +1 / -1                                                         */
+    double rho0;                  /* used when rho == NULL (fingering_periodic.py:104: 1.0)          */
+    const double *rho;            /* optional (H,ncols) host plane holding global columns [col0, col0+ncols)
+                                     which must cover the slab; entries at solid cells are ignored   */
+    int32_t col0, ncols;
+} fdlbm_init;
+int fdlbm_init_state(fdlbm_engine *e, const fdlbm_init *spec);
 
 /* Advance n reference iterations (fingering_periodic.py:455-479).  Asynchronous on the engine stream. */
 int fdlbm_step(fdlbm_engine *e, int n);
@@ -125,7 +149,9 @@ int fdlbm_halo_regions(fdlbm_engine *e, fdlbm_halo *out);
 
 /* Exact restart (absent in the reference, whose runs keep everything in RAM): the raw device state --
  * current lattice with ghosts, psi, macroscopic scratch, counters -- as an opaque blob.  A run continued
- * from a loaded checkpoint is bit-identical to the uninterrupted run.  Geometry is not part of the blob. */
+ * from a loaded checkpoint is bit-identical to the uninterrupted run.  Geometry is not part of the blob.
+ * Peer-attached slabs: every engine of the run saves / loads at the SAME step, and a barrier between the loads and
+ * the next fdlbm_step keeps a neighbour's halo stores out of a lattice that is still being restored. */
 size_t fdlbm_checkpoint_bytes(const fdlbm_engine *e);
 int fdlbm_checkpoint_save(fdlbm_engine *e, void *host, size_t bytes);
 int fdlbm_checkpoint_load(fdlbm_engine *e, const void *host, size_t bytes);

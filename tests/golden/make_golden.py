@@ -194,6 +194,36 @@ def make_fp_full():
     np.savez_compressed(os.path.join(OUT, "fp_full_scalars.npz"), **d)
 
 
+def fp_default_circles():
+    circles = []
+    r, xx, count = 10, 10, 1
+    z = r + xx - 25
+    while True:
+        if count * (xx + r) - z > 380:
+            break
+        for i in range(FP.block_num):
+            circles.append(((count * (r + xx) - z, (2 * i + 1) * (r + xx)), r))
+        count += 2
+    return circles
+
+
+def time_fp_default(steps=12, warmup=2):
+    """Wall time of the UNMODIFIED reference loop body on config 1 as shipped (400x400, 90 circles): bench.py's
+    `numpy_reference_mlups`.  NumPy ufuncs run on one thread: 1 core."""
+    import time
+    H, W = 400, 400
+    cm, mask, bb, bpa, sl, cl, vl = fp_setup(H, W, fp_default_circles())
+    for _ in range(warmup):
+        fp_iteration(cm, mask, bb, sl, cl, vl)
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        fp_iteration(cm, mask, bb, sl, cl, vl)
+    dt = time.perf_counter() - t0
+    return {"value": H * W * steps / dt / 1e6, "unit": "MLUPS", "grid": "400x400 (config 1 as shipped)", "steps": steps,
+            "ms_per_step": dt / steps * 1e3, "cores": "1 of %d" % (os.cpu_count() or 1),
+            "what": "fingering_periodic.py:455-479 executed from /root/reference, unmodified (print calls dropped)"}
+
+
 # ----------------------------------------------------------------------------------------------
 # config 3: fingering.py
 # ----------------------------------------------------------------------------------------------

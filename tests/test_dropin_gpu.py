@@ -203,3 +203,113 @@ def test_fingering_periodic_gpu_twin_against_the_oracle():
     for k in ("rho", "ux", "uy", "p", "mu"):
         assert hp.rel_err(cm._full(getattr(cm, k)), np.where(mask, want[k], 0.0)) <= TOL, k
     assert hp.rel_err(cm.f, want["f"]) <= TOL and hp.rel_err(cm.g, want["g"]) <= TOL
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# The reference's loop BODY, statement for statement, driven through the twins' per-operation methods (not
+# run_loop): what a user gets who keeps the reference's main() and only swaps the imports.
+# ---------------------------------------------------------------------------------------------------------------
+def _fp_fg_iteration(mod, cm, mask, bb_step):
+    import copy
+    for j in range(9):                                   # fingering_periodic.py:455-460, fingering.py:559-564
+        cm.F[j] = cm.getLarge_F(j)
+        cm.feq[j] = cm.getfeq(j)
+        cm.geq[j] = cm.getgeq(j)
+        cm.f[j][mask] = cm.getF(j)
+        cm.g[j][mask] = cm.getG(j)
+    f_behind = copy.deepcopy(cm.f)                       # :464-465
+    g_behind = copy.deepcopy(cm.g)
+    mod.stream(cm.f, cm.g)                               # :466
+    bb_step(f_behind, g_behind)                          # :467 / fingering.py:572-573
+    cm.zou_he_boundary_inlet()                           # :468-479
+    cm.zou_he_boundary_outlet()
+    cm.rho = cm.getRho()
+    cm.udpatePsi()
+    cm.nabla_psix = cm.getNabla_psix()
+    cm.nabla_psiy = cm.getNabla_psiy()
+    cm.nabla_psi2 = cm.getNabla_psi2()
+    cm.mu = cm.getMu()
+    cm.ux = cm.getUx()
+    cm.uy = cm.getUy()
+    cm.p = cm.getP()
+    cm.mix_tau = cm.getMix_tau()
+
+
+def test_reference_loop_body_verbatim_through_the_fp_twin(golden, monkeypatch):
+    from fingering_dynamics_b200.lattice_boltzmann import fingering_periodic as FP
+    from fingering_dynamics_b200.lattice_boltzmann.create_block import Createblock
+    from fingering_dynamics_b200.lattice_boltzmann.bounce_back import Bounce_back
+    d = golden("fp_small")
+    monkeypatch.setattr(FP, "H", int(d["H"]))
+    monkeypatch.setattr(FP, "W", int(d["W"]))
+    circles = [((int(c[0]), int(c[1])), int(c[2])) for c in d["circles"]]
+    bpa, side_list, concave_list, convex_list = Createblock(FP.H, FP.W).setCirleblock(circles)
+    mask = np.logical_not(bpa == 1)
+    bb = Bounce_back(FP.H, FP.W)
+    cm = FP.Compute(mask)
+    for it in (1, 2, 3):
+        _fp_fg_iteration(FP, cm, mask, lambda fb, gb: bb.halfway_bounceback_circle(side_list, concave_list, convex_list,
+                                                                                   fb, gb, cm.f, cm.g))
+        if it <= 2:
+            _check_compute(cm, d, "s%d" % it, mask)
+    # third iteration: against the engine (the fixtures hold s1, s2, s10, s40)
+    e = hp.fp_engine(d)
+    e.set_state(**hp.state_for_engine(d, "s0"))
+    e.step(3)
+    got = e.get_state(("f", "g", "psi", "rho"))
+    e.close()
+    assert hp.rel_err(cm.f, got["f"]) <= TOL and hp.rel_err(cm.g, got["g"]) <= TOL and hp.rel_err(cm.psi, got["psi"]) <= TOL
+    assert hp.rel_err(_masked_full(mask, cm.rho), got["rho"]) <= TOL
+
+
+def test_reference_loop_body_verbatim_through_the_fg_twin(golden, monkeypatch):
+    from fingering_dynamics_b200.lattice_boltzmann import fingering as FG
+    from fingering_dynamics_b200.lattice_boltzmann.create_block import Createblock
+    from fingering_dynamics_b200.lattice_boltzmann.bounce_back import Bounce_back
+    d = golden("fg_small")
+    monkeypatch.setattr(FG, "H", int(d["H"]))
+    monkeypatch.setattr(FG, "W", int(d["W"]))
+    rects = [((int(r[0]), int(r[1])), (int(r[2]), int(r[3]))) for r in d["rects"]]
+    bpa, corner_list = Createblock(FG.H, FG.W).setblock(rects)
+    mask = np.logical_not(bpa == 1)
+    bb = Bounce_back(FG.H, FG.W)
+    np.random.seed(7)
+    cm = FG.Compute(mask)
+
+    def bb_step(f_behind, g_behind):                     # fingering.py:572-573
+        bb.halfway_bounceback_rec(corner_list, f_behind, g_behind, cm.f, cm.g)
+        FG.bottom_top_wall(f_behind[:, 1:-1], g_behind[:, 1:-1], cm.f[:, 1:-1], cm.g[:, 1:-1])
+
+    for it in (1, 2):
+        _fp_fg_iteration(FG, cm, mask, bb_step)
+        _check_compute(cm, d, "s%d" % it, mask)
+
+
+def test_reference_loop_body_verbatim_through_the_va_twin(golden, monkeypatch):
+    import copy
+    from fingering_dynamics_b200.lattice_boltzmann import validation as VA
+    d = golden("va_small")
+    monkeypatch.setattr(VA, "H", int(d["H"]))
+    monkeypatch.setattr(VA, "W", int(d["W"]))
+    monkeypatch.setattr(VA, "psi_wall", 0.0)
+    cm = VA.Compute()
+    mask = np.ones((VA.H, VA.W), dtype=bool)
+    for it in (1, 2):                                    # validation.py:392-409
+        for j in range(9):
+            cm.feq[j] = cm.getfeq(j)
+            cm.geq[j] = cm.getgeq(j)
+        cm.mix_tau = cm.getMix_tau()
+        for j in range(9):
+            cm.F[j] = cm.getLarge_F(j)
+        cm.updateF()
+        cm.updateG()
+        f_behind = copy.deepcopy(cm.f)
+        g_behind = copy.deepcopy(cm.g)
+        VA.stream(cm.f, cm.g)
+        VA.halfway_bounceback(f_behind, g_behind, cm.f, cm.g)
+        cm.updateRho()
+        cm.updatePsi()
+        cm.updateMu()
+        cm.updateU()
+        cm.updateP()
+        _check_compute(cm, d, "s%d" % it, mask, skip=("mix_tau", "nabla_psix", "nabla_psiy"))

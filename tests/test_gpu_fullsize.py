@@ -181,3 +181,74 @@ def test_grid_wider_than_65535_columns_matches_the_oracle():
             r = ref[k] if k == "psi" else np.where(fluid, ref[k], 0.0)
             err = np.max(np.abs(got[k] - r)) / max(np.max(np.abs(r)), 1e-300)
             assert err <= 1e-10, (kernel, k, err)
+
+
+def test_benchmark_generator_matches_the_oracle_at_1024x512():
+    """the benchmark workload's own generator (radii 8-12 with centre jitter: class masks the
+    r = 10 circles of config 1 never produce) at 1024 x 512, fused fp64 engine against the ORACLE after 1, 10 and 100
+    iterations; started once from host arrays (fdlbm_set_state) and once from the device-side Compute.__init__."""
+    from oracle import oracle as orc
+    from fingering_dynamics_b200 import Engine, synthetic as syn, geometry as geo
+    from fingering_dynamics_b200.lattice_boltzmann.create_block import Createblock
+    H, W = 512, 1024
+    c = syn.fp_constants(H)
+    bpa, side, cave, vex = Createblock(H, W).setCirleblock(syn.porous_circles(H, W))
+    solid, refl = syn.porous_geometry(H, W)
+    assert np.array_equal(solid, geo.solid_from_block_psi(bpa)) and np.array_equal(refl, geo.reflect_bits_circle(side, cave, vex))
+    mask = bpa != 1
+    P = orc.make_params(H, W, tau=c["tau"], gamma=c["gamma"], a=c["a"], kappa=c["kappa"], Eta_n=c["Eta_n"], M=c["M"],
+                        psi_wall=c["psi_wall"])
+    s0 = orc.fp_initial_state(P, mask)
+    run = orc.Run(P, s0, mask=mask, circ_masks=np.stack(list(side) + list(cave) + list(vex)).astype(np.uint8), zou_he=1,
+                  inlet_ux=c["inlet_ux"], outlet_ux=c["outlet_ux"])
+    engs = {}
+    for how in ("host", "device"):
+        e = Engine(H, W, tau=c["tau"], gamma=c["gamma"], a=c["a"], kappa=c["kappa"], Eta_n=c["Eta_n"], M=c["M"],
+                   psi_wall=c["psi_wall"], zou_he="fp", inlet_ux=c["inlet_ux"], outlet_ux=c["outlet_ux"], kernel="fused")
+        e.set_geometry(solid, refl)
+        if how == "host":
+            e.set_state(**syn.fp_initial_state(solid, c))
+        else:
+            e.init_state("fp", rho0=c["rho0"])
+        engs[how] = e
+    done = 0
+    for n in (1, 10, 100):
+        ref = run.iterate(n - done)
+        for how, e in engs.items():
+            e.step(n - done)
+            got = e.get_state(("psi", "rho", "ux", "uy"))
+            for k in got:
+                r = ref[k] if k == "psi" else np.where(mask, ref[k], 0.0)
+                err = np.max(np.abs(got[k] - r)) / np.max(np.abs(r))
+                assert err <= 1e-10, (how, n, k, err)
+        done = n
+    for e in engs.values():
+        e.close()
+
+
+def test_fp32_packed_kernel_at_8192x2048():
+    """configs[3] in fp32: the packed two-row kernel against the fp32 two-pass kernel (same arithmetic, other rounding
+    order: 5e-5 of the field maximum) and against the fp64 engine within the stated fp32 tolerance (psi, rho 2e-5,
+    u 2e-3 of max |u|), 6 steps from the device-side initial state; sign(psi) agrees wherever |psi| > 1e-3."""
+    from fingering_dynamics_b200 import Engine, synthetic as syn
+    H, W = 2048, 8192
+    c = syn.fp_constants(H)
+    solid, refl = syn.porous_geometry(H, W)
+    res = {}
+    for tag, dtype, kernel in (("f32", "f32", "fused"), ("f32_2p", "f32", "twopass"), ("f64", "f64", "fused")):
+        e = Engine(H, W, tau=c["tau"], gamma=c["gamma"], a=c["a"], kappa=c["kappa"], Eta_n=c["Eta_n"], M=c["M"],
+                   psi_wall=c["psi_wall"], zou_he="fp", inlet_ux=c["inlet_ux"], outlet_ux=c["outlet_ux"], dtype=dtype,
+                   kernel=kernel)
+        e.set_geometry(solid, refl)
+        e.init_state("fp", rho0=c["rho0"])
+        e.step(6)
+        res[tag] = e.get_state(("psi", "rho", "ux", "uy"))
+        e.close()
+    for k in ("psi", "rho", "ux", "uy"):
+        a, b, d = res["f32"][k], res["f32_2p"][k], res["f64"][k]
+        scale = np.max(np.abs(d)) if k in ("psi", "rho") else max(np.max(np.abs(res["f64"]["ux"])), np.max(np.abs(res["f64"]["uy"])))
+        assert np.max(np.abs(a - b)) <= 5e-5 * max(1.0, np.max(np.abs(b))), ("packed vs two-pass", k, np.max(np.abs(a - b)))
+        tol = 2e-5 if k in ("psi", "rho") else 2e-3
+        assert np.max(np.abs(a - d)) <= tol * scale, ("fp32 vs fp64", k, np.max(np.abs(a - d)), scale)
+    sure = np.abs(res["f64"]["psi"]) > 1e-3
+    assert np.array_equal(np.sign(res["f32"]["psi"][sure]), np.sign(res["f64"]["psi"][sure]))

@@ -241,3 +241,149 @@ def test_peer_halo_slabs_of_a_porous_grid_match_the_single_slab_run(dtype, perio
             assert np.array_equal(got[k], want[k][..., x0:x1]), (dtype, periodic, r, k)
     for e in engs:
         e.close()
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# the path the multi-GPU bench times: one PROCESS per slab, neighbours' lattices and flag words mapped with CUDA IPC
+# (fdlbm_peer_export / fdlbm_peer_attach, the cudaIpcOpenMemHandle branch), steps ordered across processes by
+# cuStreamWriteValue32 / cuStreamWaitValue32.  All processes share cuda:0, so this runs on the 1-GPU test box.
+# ---------------------------------------------------------------------------------------------------------------
+ALL12 = ("f", "g", "psi", "rho", "ux", "uy", "p", "mu", "mix_tau", "nabla_psix", "nabla_psiy", "nabla_psi2")
+OUT6 = ("f", "g", "psi", "rho", "ux", "uy")
+
+
+def _porous_case(dtype, periodic):
+    from fingering_dynamics_b200 import synthetic as syn
+    H, W = 256, 192
+    c = syn.fp_constants(H)
+    solid, refl = syn.porous_geometry(H, W)
+    st = syn.fp_initial_state(solid, c)
+    kw = dict(tau=c["tau"], gamma=c["gamma"], a=c["a"], kappa=c["kappa"], Eta_n=c["Eta_n"], M=c["M"], psi_wall=c["psi_wall"],
+              dtype=dtype)
+    if periodic:
+        kw.update(zou_he="none", x_periodic=True)
+    else:
+        kw.update(zou_he="fp", inlet_ux=c["inlet_ux"], outlet_ux=c["outlet_ux"])
+    return H, W, solid, refl, st, kw
+
+
+def _ipc_worker(rank, world, port, dtype, periodic, q):
+    try:
+        os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+        sys.path.insert(0, ROOT)
+        import torch.distributed as dist
+        from fingering_dynamics_b200 import Engine
+        from fingering_dynamics_b200.slab import SlabRunner, slab_bounds
+        dist.init_process_group("gloo", rank=rank, world_size=world)
+        H, W, solid, refl, st, kw = _porous_case(dtype, periodic)
+        x0, x1 = slab_bounds(W, world, rank)
+        sl = (Ellipsis, slice(x0, x1))
+        bad = []
+
+        def same(got, want, tag):
+            for k in got:
+                if not np.array_equal(got[k], want[k][sl]):
+                    bad.append("%s:%s" % (tag, k))
+
+        # the single-engine run every rank compares its slab with
+        ref = Engine(H, W, **kw)
+        ref.set_geometry(solid, refl)
+        ref.set_state(**st)
+        ref.step(12)
+        want12 = ref.get_state(ALL12)
+        ref.set_state(**want12)          # restart from a mid-run state: populations inside solids are non-zero now
+        ref.step(5)
+        want17 = ref.get_state(OUT6)
+        ref.step(3)
+        want20 = ref.get_state(OUT6)
+        ref.close()
+
+        eng = Engine(H, W, slab=(x0, x1), external_halo=True, **kw)
+        eng.set_geometry(solid, refl)
+        run = SlabRunner(eng, rank, world, periodic=periodic, halo="peer")   # IPC handles travel over gloo
+        run.set_state(**st)
+        for n in (1, 4, 7):              # many steps per call: only the stream flags order the processes
+            run.step(n)
+        same(run.get_state(OUT6), want12, "step12")
+        run.set_state(**want12)          # k_collide_first must push the solid cells of the edge columns too
+        run.step(5)
+        same(run.get_state(OUT6), want17, "restart17")
+        blob = run.checkpoint()          # waits for the neighbours' halo stores of step 17
+        run.step(3)
+        same(run.get_state(OUT6), want20, "step20")
+        run.restore(blob)
+        run.step(3)
+        same(run.get_state(OUT6), want20, "restored20")
+        eng.sync()
+        dist.barrier()
+        eng.close()
+        dist.destroy_process_group()
+        q.put((rank, bad))
+    except Exception as ex:  # noqa: BLE001
+        import traceback
+        q.put((rank, ["exception: %s\n%s" % (ex, traceback.format_exc())]))
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("world,dtype,periodic", [(2, "f64", False), (3, "f64", False), (2, "f32", False), (3, "f32", False),
+                                                   (2, "f64", True), (3, "f32", True)])
+def test_peer_halo_across_processes_is_bit_identical_to_one_engine(world, dtype, periodic):
+    """one process per slab on cuda:0, IPC-mapped halos: step(1); step(4); step(7), a restart from the step-12 state,
+    a checkpoint / restore in peer mode -- every slab bitwise equal to the single-engine run"""
+    import torch.multiprocessing as mp
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 29800 + (os.getpid() % 400) + 3 * world + (1 if periodic else 0) + (50 if dtype == "f32" else 0)
+    procs = [ctx.Process(target=_ipc_worker, args=(r, world, port, dtype, periodic, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    try:
+        res = [q.get(timeout=300) for _ in procs]
+    finally:
+        for p in procs:
+            p.join(timeout=30)
+            if p.is_alive():
+                p.kill()
+    for rank, bad in sorted(res):
+        assert not bad, "rank %d: %s" % (rank, "; ".join(bad))
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("dtype", ["f64", "f32"])
+def test_peer_slabs_restart_from_a_mid_run_state(dtype):
+    """same-process variant of the restart above: get_state at step 12 -> set_state -> 5 steps on three peer slabs"""
+    from fingering_dynamics_b200 import Engine
+    from fingering_dynamics_b200.slab import slab_bounds
+    H, W, solid, refl, st, kw = _porous_case(dtype, False)
+    nslab = 3
+    ref = Engine(H, W, **kw)
+    ref.set_geometry(solid, refl)
+    ref.set_state(**st)
+    ref.step(12)
+    mid = ref.get_state(ALL12)
+    assert np.abs(mid["f"][:, solid != 0]).max() > 0     # the point of the test: solids hold streamed populations
+    ref.set_state(**mid)
+    ref.step(5)
+    want = ref.get_state(OUT6)
+    ref.close()
+    engs = [Engine(H, W, slab=slab_bounds(W, nslab, r), external_halo=True, **kw) for r in range(nslab)]
+    for e in engs:
+        e.set_geometry(solid, refl)
+    infos = [e.peer_export() for e in engs]
+    for r, e in enumerate(engs):
+        if r > 0:
+            e.peer_attach(0, infos[r - 1])
+        if r < nslab - 1:
+            e.peer_attach(1, infos[r + 1])
+    for e in engs:
+        e.set_state(**mid)
+    for e in engs:
+        e.sync()
+    for e in engs:
+        e.step(5)
+    for r, e in enumerate(engs):
+        x0, x1 = slab_bounds(W, nslab, r)
+        got = e.get_state(OUT6)
+        for k in got:
+            assert np.array_equal(got[k], want[k][..., x0:x1]), (dtype, r, k)
+        e.close()
