@@ -4,6 +4,7 @@
 
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <unistd.h>
 #include <string>
@@ -40,7 +41,6 @@ int fail(int code, const char *fmt, ...)
     } while (0)
 
 enum { ST_EMPTY = 0, ST_PRE = 1, ST_POST = 2 };
-constexpr int STEAL_CAP = 1 << 16;  // CTAs the work table of the stealing build has room for
 
 }  // namespace
 
@@ -68,7 +68,7 @@ struct fdlbm_engine {
     int peer_Wl[2] = {0, 0};
     bool peer_ipc[2] = {false, false};
     uint32_t peer_step = 0;                                   // steps taken in peer mode (never reset)
-    int *steal_tab = nullptr;                                 // work table of the -DFDLBM_STEAL=1 build
+    ChunkBalancer balancer;                                   // measured column chunks of the fused step (lbm_fused.cuh)
     int cur = 0, pcur = 0;
     int state = ST_EMPTY;
     bool have_geometry = false;
@@ -118,8 +118,11 @@ LbmParams<T> make_params(const fdlbm_engine *e, int src, int psrc)
     P.f3coef = (T)c.outlet_f3_coef;
     P.peer_lo = P.peer_hi = nullptr;
     P.peer_lo_Wl = 0;
-    P.steal = nullptr;
-    P.steal_cap = 0;
+    P.chunk_tab = nullptr;
+    P.chunk_tab_next = nullptr;
+    P.cta_ticks = nullptr;
+    P.cta_done = nullptr;
+    P.chunk_alpha = 0.f;
     return P;
 }
 
@@ -245,11 +248,7 @@ int launch_step(fdlbm_engine *e, bool finalize)
             k_step_twopass<T, false><<<cell_grid(e, e->Wl), TPB, 0, e->stream>>>(P, field_ptrs<T>(e));
         e->launches += 2;
     } else {
-#if FDLBM_STEAL && !defined(FDLBM_STEAL_DRY)  // FDLBM_STEAL_DRY: the stealing build with its table switched off (A/B of the loop structure)
-        P.steal = e->steal_tab;
-        P.steal_cap = STEAL_CAP;
-#endif
-        int rc = launch_fused_auto<T>(P, e->stream);
+        int rc = launch_fused_auto<T>(P, e->stream, &e->balancer);
         if (rc) return fail(FDLBM_E_CUDA, "fused launch configuration failed (%d)", rc);
         e->launches += 1;
     }
@@ -559,10 +558,23 @@ int fdlbm_create(const fdlbm_config *cfg, fdlbm_engine **out)
         CUE(cudaMalloc(&e->psi[k], e->plane_elems() * e->esize));
         CUE(cudaMemsetAsync(e->psi[k], 0, e->plane_elems() * e->esize, e->stream));
     }
-#if FDLBM_STEAL
-    CUE(cudaMalloc((void **)&e->steal_tab, 5 * STEAL_CAP * sizeof(int)));
-    CUE(cudaMemsetAsync(e->steal_tab, 0, 5 * STEAL_CAP * sizeof(int), e->stream));
-#endif
+    {
+        // balancer buffers: two boundary tables, per-CTA durations, the completion counter
+        ChunkBalancer &B = e->balancer;
+        const size_t n = 2 * ChunkBalancer::CAP_TAB + ChunkBalancer::CAP_CTA + 64;
+        CUE(cudaMalloc((void **)&B.tab[0], n * sizeof(int)));
+        CUE(cudaMemsetAsync(B.tab[0], 0, n * sizeof(int), e->stream));
+        B.tab[1] = B.tab[0] + ChunkBalancer::CAP_TAB;
+        B.ticks = (unsigned *)(B.tab[1] + ChunkBalancer::CAP_TAB);
+        B.done = B.ticks + ChunkBalancer::CAP_CTA;
+        auto env_int = [](const char *name, int dflt) {
+            const char *v = getenv(name);
+            return v && *v ? atoi(v) : dflt;
+        };
+        B.enabled = env_int("FDLBM_BALANCE", 1) != 0;
+        B.measure_first = env_int("FDLBM_BALANCE_FIRST", B.measure_first);
+        B.measure_every = env_int("FDLBM_BALANCE_EVERY", B.measure_every);
+    }
     CUE(cudaMalloc((void **)&e->flags, 256));
     CUE(cudaMemsetAsync(e->flags, 0, 256, e->stream));
     // the flag arrays carry one spare (zero) column: the step kernels load flags three columns ahead without a bound check
@@ -603,7 +615,7 @@ void fdlbm_destroy(fdlbm_engine *e)
             cudaIpcCloseMemHandle(e->peer_flags[side]);
         }
     void *ptrs[] = {e->lat[0], e->lat[1], e->psi[0], e->psi[1], e->fields, e->reflect, e->solid_bytes,
-                    e->solid, e->inlet, e->outlet, e->staging, e->flags, e->steal_tab};
+                    e->solid, e->inlet, e->outlet, e->staging, e->flags, e->balancer.tab[0]};
     for (void *p : ptrs)
         if (p) cudaFree(p);
     if (e->stream) cudaStreamDestroy(e->stream);
@@ -877,9 +889,26 @@ int fdlbm_peer_attach(fdlbm_engine *e, int side, const fdlbm_peer_info *nb)
     return 0;
 }
 
-#ifdef FDLBM_CTA_TIMES  // profiling build only (not part of include/fdlbm.h)
-int fdlbm_debug_cta_times(void *host, size_t bytes) { return (int)cudaMemcpyFromSymbol(host, fdlbm::g_cta_times, bytes); }
-#endif
+int fdlbm_balance_info(fdlbm_engine *e, int32_t *nyt, int32_t *nchunks, int32_t *bounds, uint32_t *ticks_ns, int cap)
+{
+    if (!e || !nyt || !nchunks) return fail(FDLBM_E_ARG, "null argument");
+    CU(cudaSetDevice(e->cfg.device));
+    CU(cudaStreamSynchronize(e->stream));
+    const ChunkBalancer &B = e->balancer;
+    *nyt = B.nyt;
+    *nchunks = B.nyt > 0 ? B.grid / B.nyt : 0;
+    if (B.cur < 0 || B.nyt <= 0) return 0;  // equal chunks so far
+    const int ntab = B.nyt * (*nchunks + 1);
+    if (bounds) {
+        if (cap < ntab) return fail(FDLBM_E_ARG, "bounds needs %d entries", ntab);
+        CU(cudaMemcpy(bounds, B.tab[B.cur], (size_t)ntab * sizeof(int), cudaMemcpyDeviceToHost));
+    }
+    if (ticks_ns) {
+        if (cap < B.grid) return fail(FDLBM_E_ARG, "ticks_ns needs %d entries", B.grid);
+        CU(cudaMemcpy(ticks_ns, B.ticks, (size_t)B.grid * sizeof(unsigned), cudaMemcpyDeviceToHost));
+    }
+    return 0;
+}
 
 void *fdlbm_pinned_alloc(size_t bytes)
 {

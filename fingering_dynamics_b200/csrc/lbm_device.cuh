@@ -37,9 +37,14 @@ struct LbmParams {
     // two edge columns straight into their ghost columns (halo exchange fused into the step)
     T *peer_lo, *peer_hi;
     int peer_lo_Wl;           // owned columns of the low-side neighbour (its high ghosts are columns Wl, Wl+1)
-    // work table of the column-range stealing build (-DFDLBM_STEAL=1): {end, next column} per CTA, or nullptr
-    int *steal;
-    int steal_cap;            // CTAs the table has room for
+    // measured column chunks of the fused fp64 step (lbm_fused.cuh, "balancer"): boundaries this launch uses
+    // ([strip][chunk + 1], nullptr = equal chunks) and, on a measuring launch, where the CTA that finishes last
+    // writes the boundaries for the next launch from the CTA durations of this one
+    const int *chunk_tab;
+    int *chunk_tab_next;
+    unsigned *cta_ticks;      // [CTA] duration in ns of each CTA of a measuring launch
+    unsigned *cta_done;       // CTAs finished so far (reset by the last one)
+    float chunk_alpha;        // damping of a rebalancing step
 };
 
 // macroscopic outputs of the finalize pass / inputs of the first collision, each [(xl+G)*Hp + y]

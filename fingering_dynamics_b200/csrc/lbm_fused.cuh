@@ -24,34 +24,6 @@
 
 namespace fdlbm {
 
-#ifdef FDLBM_CTA_TIMES  // profiling build (gpurun_in/cta_times.py): per-CTA start / end time, SM and strip
-__device__ unsigned long long g_cta_times[4096 * 4];
-struct CtaTimer {
-    unsigned long long t0 = 0;
-    unsigned smid = 0;
-    __device__ __forceinline__ CtaTimer()
-    {
-        if (threadIdx.x == 0) {
-            asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
-            asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
-        }
-    }
-    __device__ __forceinline__ void stop(int tag) const
-    {
-        if (threadIdx.x == 0 && blockIdx.x < 4096) {
-            unsigned long long t1;
-            asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1));
-            unsigned long long *r = g_cta_times + 4 * blockIdx.x;
-            r[0] = t0, r[1] = t1, r[2] = smid, r[3] = (unsigned long long)tag;
-        }
-    }
-};
-#else
-struct CtaTimer {
-    __device__ __forceinline__ void stop(int) const {}
-};
-#endif
-
 #ifndef FDLBM_FUSED_TY
 #define FDLBM_FUSED_TY 128
 #endif
@@ -134,40 +106,6 @@ __device__ __forceinline__ void mbar_wait(void *bar, unsigned parity)
         : "memory");
 }
 
-#ifndef FDLBM_STEAL
-#define FDLBM_STEAL 0  // 1: a CTA that has finished its column range takes over half of the slowest same-strip CTA's rest
-#endif
-#ifndef FDLBM_STEAL_MIN
-#define FDLBM_STEAL_MIN 12
-#endif
-constexpr int STEAL_MIN = FDLBM_STEAL_MIN;  // columns a range must still have for a steal to pay for its 3-column warm-up
-#ifndef FDLBM_STEAL_EVERY
-#define FDLBM_STEAL_EVERY 1  // progress is published and the end marker fetched every so many columns (a power of two)
-#endif
-constexpr int STEAL_EVERY = FDLBM_STEAL_EVERY;
-static_assert(STEAL_EVERY > 0 && (STEAL_EVERY & (STEAL_EVERY - 1)) == 0, "FDLBM_STEAL_EVERY must be a power of two");
-// columns a victim may run past a lowered end marker: it reads the marker fetched one block of STEAL_EVERY columns ago,
-// and its published progress is up to STEAL_EVERY - 1 columns old
-constexpr int STEAL_SLACK = 3 * STEAL_EVERY - 1;
-static_assert(STEAL_MIN >= STEAL_SLACK + 8, "raise FDLBM_STEAL_MIN with FDLBM_STEAL_EVERY: a steal must leave both sides some columns");
-__device__ __forceinline__ int steal_block(int x) { return x / STEAL_EVERY; }  // x >= 0
-__device__ __forceinline__ int ld_vol(const int *p)
-{
-    int v;
-    asm volatile("ld.volatile.global.s32 %0, [%1];" : "=r"(v) : "l"(p));  // no memory clobber: a compiler barrier here
-                                                                          // serialises the f loads of the whole iteration
-    return v;
-}
-__device__ __forceinline__ void st_vol(int *p, int v) { asm volatile("st.volatile.global.s32 [%0], %1;" ::"l"(p), "r"(v)); }
-__device__ __forceinline__ void st_vol2(int *p, int a, int b)  // both words of a table entry at once
-{
-    asm volatile("st.volatile.global.v2.s32 [%0], {%1, %2};" ::"l"(p), "r"(a), "r"(b));
-}
-__device__ __forceinline__ void ld_vol2(const int *p, int &a, int &b)
-{
-    asm volatile("ld.volatile.global.v2.s32 {%0, %1}, [%2];" : "=r"(a), "=r"(b) : "l"(p));
-}
-
 template <typename T, int TY>
 struct FusedCfg {
     static constexpr int HALO = 16 / (int)sizeof(T);      // rows of apron per side: keeps 16-byte chunks aligned
@@ -232,6 +170,51 @@ __device__ __forceinline__ void pull_staged(const T *sm, const T *s0, const T *s
     v[8] = *s8;
 }
 
+// ---- balancer ------------------------------------------------------------------------------------------------
+// One resident wave ends with its slowest CTA, and the spread between CTAs is systematic: a few SMs run ~5 % slower
+// than the rest, and SMs that were handed two CTAs instead of three finish far ahead.  A MEASURING launch records
+// the duration of every CTA (%globaltimer); the CTA that finishes last turns them into new column boundaries for the
+// NEXT launch, strip by strip: each chunk's length moves towards Wl * v_c / sum(v) with v_c = columns / duration of
+// the CTA that had chunk c (CTA -> SM placement of a one-wave grid repeats from launch to launch).  Nothing is added
+// to the column loop, and results do not depend on the boundaries (every cell is computed by exactly one CTA with the
+// same arithmetic whatever its range).
+__device__ __forceinline__ unsigned long long global_ns()
+{
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    return t;
+}
+
+template <typename T, int TY>
+__device__ __noinline__ void rebalance_chunks(const LbmParams<T> &P, int nyt, int chunk)
+{
+    const int nch = (int)gridDim.x / nyt, Wl = P.Wl;
+    const int minlen = min(8, Wl / nch);
+    for (int s = threadIdx.x; s < nyt; s += TY) {
+        const int *cur = P.chunk_tab ? P.chunk_tab + (size_t)s * (nch + 1) : nullptr;
+        int *nxt = P.chunk_tab_next + (size_t)s * (nch + 1);
+        auto len_of = [&](int c) { return cur ? cur[c + 1] - cur[c] : min(Wl, (c + 1) * chunk) - c * chunk; };
+        auto speed = [&](int c) {
+            const unsigned d = __ldcg(P.cta_ticks + (size_t)c * nyt + s);
+            return (float)len_of(c) / (float)(d > 0u ? d : 1u);
+        };
+        float vsum = 0.f;
+        for (int c = 0; c < nch; ++c) vsum += speed(c);
+        float acc = 0.f;
+        int prev = 0;
+        nxt[0] = 0;
+        for (int c = 0; c < nch - 1; ++c) {
+            const float len = (float)len_of(c);
+            acc += len + P.chunk_alpha * ((float)Wl * speed(c) / vsum - len);
+            int b = (int)(acc + 0.5f);
+            b = max(b, prev + minlen);
+            b = min(b, Wl - (nch - 1 - c) * minlen);
+            nxt[c + 1] = prev = b;
+        }
+        nxt[nch] = Wl;
+    }
+}
+
 struct RawFlags {
     unsigned refl, word;  // reflect byte and solid-mask word exactly as loaded
 };
@@ -241,35 +224,28 @@ struct RawFlags {
 template <typename T, int TY, int HPC>
 __global__ void __launch_bounds__(TY, sizeof(T) == 8 ? FDLBM_FUSED_MINB64 : FDLBM_FUSED_MINB32) k_fused(const __grid_constant__ LbmParams<T> P, int nyt, int chunk)
 {
-    const CtaTimer timer;
     using C = FusedCfg<T, TY>;
     constexpr int D = FUSED_D, NS = C::NS, PT = C::PT, HALO = C::HALO, FAM = C::FAM;
     constexpr unsigned FULL = 0xffffffffu;
     extern __shared__ __align__(16) unsigned char smem_raw[];
     T *gst = reinterpret_cast<T *>(smem_raw);        // [NS][9][PT]
     __shared__ __align__(8) unsigned long long bars[NS];  // one mbarrier per g stage (bulk-copy path)
+    __shared__ unsigned long long s_t0;                   // balancer: start time of this CTA
+    __shared__ int s_last;
     const int t = threadIdx.x, lane = t & 31;
+    if (P.chunk_tab_next && t == 0) s_t0 = global_ns();
     const int H = P.H, Hp = HPC > 0 ? HPC : P.Hp;
 
     const int yt = blockIdx.x % nyt;
-#if FDLBM_STEAL
-    int xs = (blockIdx.x / nyt) * chunk;  // the column range changes when this CTA takes over part of another's
-    int xe = min(P.Wl, xs + chunk);
-    // The end of my range travels table -> shared memory with the g stages' own cp.async groups (16 bytes, L2 path):
-    // a plain load kept in flight across the loop edge makes ptxas wait for it at the loop head.
-    __shared__ __align__(16) int s_end[2][4];
-    __shared__ int s_range[2];
-    const bool steal = P.steal != nullptr && (int)gridDim.x <= P.steal_cap;
-    // end markers: one 16-byte entry per CTA (what cp.async.cg moves); progress words live in their own region -- a
-    // progress store followed by the cp.async of the SAME entry cost 17 % (store -> load on one address), apart 2 % each
-    int *const my_tab = P.steal + 4 * blockIdx.x;                       // [0] = end of my range
-    int *const my_prog = P.steal + 4 * P.steal_cap + blockIdx.x;        // the column I am working on
-    unsigned par = 0;                              // phase parity of the NS stage barriers, one bit each
-    int fill_hi = 0, wait_hi = 0;                  // highest g column whose bulk fill was issued / waited for
-#else
-    const int xs = (blockIdx.x / nyt) * chunk;
-    const int xe = min(P.Wl, xs + chunk);
-#endif
+    // Column range of this CTA: equal chunks, or -- once the engine's balancer has seen a few launches -- the
+    // boundaries it derived from the measured CTA durations (chunk_tab[yt * (nchunks + 1) + c], see rebalance below)
+    const int ck = blockIdx.x / nyt;
+    int xs_ = ck * chunk, xe_ = min(P.Wl, xs_ + chunk);
+    if (P.chunk_tab) {
+        const int *row = P.chunk_tab + (size_t)yt * (gridDim.x / nyt + 1) + ck;
+        xs_ = __ldg(row), xe_ = __ldg(row + 1);
+    }
+    const int xs = xs_, xe = xe_;
     const int y0 = yt * TY;
     const int y = y0 + t;
     const int ny = min(TY, H - y0);
@@ -312,9 +288,6 @@ __global__ void __launch_bounds__(TY, sizeof(T) == 8 ? FDLBM_FUSED_MINB64 : FDLB
     auto prefetch = [&](int v) {
         const int cg = v + 2 + D;
         if (cg >= xs - 2 && cg <= xe + 1) {
-#if FDLBM_STEAL
-            fill_hi = cg;
-#endif
             T *stage = gst + slot(cg) * FAM;
             const T *col = P.src + lat_idx(Hp, cg, 9, 0);
             if (bulk) {
@@ -342,20 +315,9 @@ __global__ void __launch_bounds__(TY, sizeof(T) == 8 ? FDLBM_FUSED_MINB64 : FDLB
     };
     // wait until g column c has landed in its stage (bulk path: the fill of column c is the
     // ((c - (xs-2)) / NS)-th use of its mbarrier, whose parity is waited for)
-#if FDLBM_STEAL
-    auto landed = [&](int c) {  // every fill is waited for exactly once: the parity of a stage barrier is a running bit
-        if (bulk) {
-            const int s_ = slot(c);
-            mbar_wait(&bars[s_], (par >> s_) & 1u);
-            par ^= 1u << s_;
-            wait_hi = c;
-        }
-    };
-#else
     auto landed = [&](int c) {
         if (bulk) mbar_wait(&bars[slot(c)], (unsigned)(((c - (xs - 2)) / NS) & 1));
     };
-#endif
     // Per-cell flags are plain global loads issued two columns ahead of their use and carried RAW in
     // registers: nothing depends on them until they are decoded two iterations later, so their latency
     // never sits on the critical path.
@@ -403,18 +365,6 @@ __global__ void __launch_bounds__(TY, sizeof(T) == 8 ? FDLBM_FUSED_MINB64 : FDLB
     const RawFlags z{0u, 0u};
     RawFlags fq0 = z, fq1 = z, eq0 = z, eq1 = z;               // look-ahead queues: own / edge-neighbour cell, columns x+1, x+2
 
-#if FDLBM_STEAL
-    for (;;) {  // one pass per column range: the CTA's own, then the ones it takes over
-    if (steal && t == 0) {
-        st_vol(my_tab, 0);      // never (old end, new progress): that pair could look like columns left to take
-        __threadfence();
-        st_vol(my_prog, xs);
-        __threadfence();
-        st_vol(my_tab, xe);
-        s_end[0][0] = s_end[1][0] = xe;  // what the first iterations read (the warm-up below has barriers)
-    }
-    fill_hi = wait_hi = xs - 3;
-#endif
     // pipeline warm-up.  Steps v = xs-4-D .. xs-2 bring in g columns xs-2 .. xs+D (all NS slots);
     // psi(xs-1) needs g columns xs-2..xs, then g column xs-2 makes room for column xs+1+D.
     for (int v = xs - 4 - D; v < xs - 1; ++v) prefetch(v);
@@ -443,37 +393,15 @@ __global__ void __launch_bounds__(TY, sizeof(T) == 8 ? FDLBM_FUSED_MINB64 : FDLB
     psi_column(xs, fl_cur, decode(re_0, ye1), g_cur, p0_m, p0_0, p0_p);
 
     for (int x = xs; x < xe; ++x) {
-#if FDLBM_STEAL
-#ifndef FDLBM_STEAL_NOSTORE
-        if (steal && t == 0 && (x & (STEAL_EVERY - 1)) == 0) st_vol(my_prog, x);  // my progress, for whoever looks for work
-#endif
-#endif
         cp_async_wait<D - 1>();  // g column x+2 has landed
         landed(x + 2);
         __syncthreads();         // ... for every thread; and everybody is done with iteration x-1
-#if FDLBM_STEAL
-        if (steal) {  // somebody took over the rest of this range from column s_end on (CTA-uniform)
-            const int en = s_end[steal_block(x) & 1][0];
-            if (en < xe) {
-                xe = en;
-                if (x >= xe) break;
-            }
-        }
-#endif
         // Decode the flags of column x+1 BEFORE any new global load is issued: they were loaded two iterations
         // ago, but the hardware scoreboard slots are shared -- decoding them after this iteration's f loads
         // would wait for those loads too (measured: 18 % of all stall samples on the first psi shuffle).
         fl_nxt = decode(fq0, y);
         unsigned fe_nxt = decode(eq0, ye1);
         asm volatile("" : "+r"(fl_nxt), "+r"(fe_nxt)::"memory");
-#if FDLBM_STEAL
-#ifndef FDLBM_STEAL_NOCP
-        // lands with g column x+3; read from the first iteration of the next block on (the other slot is read until then)
-        if (steal && t == 0 && (x & (STEAL_EVERY - 1)) == 0) cp_async16(&s_end[(steal_block(x) + 1) & 1][0], my_tab);
-#else
-        if (steal && t == 0 && (x & (STEAL_EVERY - 1)) == 0) s_end[(steal_block(x) + 1) & 1][0] = xe;
-#endif
-#endif
         prefetch(x);             // overwrites the stage of g column x-1: no longer read
         T f[9];
         {
@@ -523,51 +451,20 @@ __global__ void __launch_bounds__(TY, sizeof(T) == 8 ? FDLBM_FUSED_MINB64 : FDLB
         eq0 = eq1, eq1 = eq2;
     }
     cp_async_wait<0>();
-#if FDLBM_STEAL
-    if (bulk)
-        for (int c = wait_hi + 1; c <= fill_hi; ++c) landed(c);  // fills issued before the range was cut short
-    if (!steal) break;
-    if (t == 0) st_vol(my_prog, 0x3fffffff);  // nothing left to take from me
-    __syncthreads();                             // everybody is done with the stages of this range
-    if (t < 32) {
-        // warp 0: the same-strip CTA with the most columns left hands over the second half of them.  Columns that
-        // end up processed twice (stale progress, races between thieves) are written with identical values.
-        const int nchunks = (int)gridDim.x / nyt;
-        int nxs = -1, nxe = -1;
-        for (int attempt = 0; attempt < 3 && nxs < 0; ++attempt) {
-            int brem = 0, bc = -1;
-            for (int c = lane; c < nchunks; c += 32) {
-                const int k2 = c * nyt + yt;
-                const int e_ = ld_vol(P.steal + 4 * k2), p_ = ld_vol(P.steal + 4 * P.steal_cap + k2);
-                if (e_ - p_ > brem) brem = e_ - p_, bc = c;
-            }
-#pragma unroll
-            for (int o = 16; o; o >>= 1) {
-                const int r2 = __shfl_xor_sync(FULL, brem, o), c2 = __shfl_xor_sync(FULL, bc, o);
-                if (r2 > brem || (r2 == brem && c2 > bc)) brem = r2, bc = c2;
-            }
-            if (brem < STEAL_MIN) break;
-            if (lane == 0) {
-                int *vt = P.steal + 4 * (bc * nyt + yt);
-                const int e_ = ld_vol(vt), p_ = ld_vol(P.steal + 4 * P.steal_cap + bc * nyt + yt);
-                if (e_ - p_ >= STEAL_MIN) {
-                    const int ne = p_ + STEAL_SLACK + (e_ - p_ - STEAL_SLACK + 1) / 2;  // the victim keeps the first half
-                    // only if the victim still works on the range just read (it may have moved on to another one)
-                    if (atomicCAS(vt, e_, ne) == e_) nxs = ne, nxe = e_;
-                }
-            }
-            nxs = __shfl_sync(FULL, nxs, 0);
-            nxe = __shfl_sync(FULL, nxe, 0);
+    if (P.chunk_tab_next) {  // measuring launch (CTA-uniform)
+        __syncthreads();
+        if (t == 0) {
+            P.cta_ticks[blockIdx.x] = (unsigned)(global_ns() - s_t0);
+            __threadfence();
+            s_last = atomicAdd(P.cta_done, 1u) == gridDim.x - 1;
         }
-        if (lane == 0) s_range[0] = nxs, s_range[1] = nxe;
+        __syncthreads();
+        if (s_last) {
+            __threadfence();
+            rebalance_chunks<T, TY>(P, nyt, chunk);
+            if (t == 0) *P.cta_done = 0u;
+        }
     }
-    __syncthreads();
-    xs = s_range[0];
-    xe = s_range[1];
-    if (xs < 0) break;
-    }  // for (;;) over column ranges
-#endif
-    timer.stop(yt);
 }
 
 // Column chunk length for `nyt` strips on `n_cta` resident CTA slots.  With c chunks per strip the kernel takes
@@ -592,10 +489,24 @@ inline int fused_chunk(int nyt, int n_cta, int Wl)
     return chunk < 8 ? 8 : chunk;
 }
 
+// host side of the balancer: device buffers owned by the engine + what the next launch should do
+struct ChunkBalancer {
+    static constexpr int CAP_CTA = 2048, CAP_TAB = 4096;
+    int *tab[2] = {nullptr, nullptr};  // boundary tables, read / written alternately
+    unsigned *ticks = nullptr, *done = nullptr;
+    bool enabled = false;
+    int cur = -1;                      // table holding valid boundaries, -1: none yet (equal chunks)
+    int grid = 0, nyt = 0;             // launch shape the boundaries belong to
+    long launches = 0;                 // fused launches of that shape so far
+    int measure_first = 12;            // every one of the first launches measures and rebalances (damping 0.7) ...
+    int measure_every = 64;            // ... then one in so many (damping 0.3); 0: never again
+};
+
 // returns 0 or a cudaError_t
 template <typename T, int HPC>
-int launch_fused_hp(const LbmParams<T> &P, cudaStream_t stream)
+int launch_fused_hp(const LbmParams<T> &P_, cudaStream_t stream, ChunkBalancer *B)
 {
+    LbmParams<T> P = P_;
     using C = FusedCfg<T, FUSED_TY>;
     auto kern = k_fused<T, FUSED_TY, HPC>;
     // resident CTA slots, cached per device (the shared-memory attribute is a per-device setting too)
@@ -619,23 +530,41 @@ int launch_fused_hp(const LbmParams<T> &P, cudaStream_t stream)
     const int nyt = (P.H + FUSED_TY - 1) / FUSED_TY;
     const int chunk = fused_chunk(nyt, n_cta, P.Wl);
     const int nchunks = (P.Wl + chunk - 1) / chunk;
-    kern<<<nyt * nchunks, FUSED_TY, C::SMEM, stream>>>(P, nyt, chunk);
+    const int grid = nyt * nchunks;
+    P.chunk_tab = nullptr;
+    P.chunk_tab_next = nullptr;
+    // measured chunk boundaries: only where the whole grid is ONE resident wave (CTA -> SM placement repeats)
+    if (B && B->enabled && nchunks > 1 && grid <= n_cta && grid <= ChunkBalancer::CAP_CTA && grid + nyt <= ChunkBalancer::CAP_TAB) {
+        if (B->grid != grid || B->nyt != nyt) B->grid = grid, B->nyt = nyt, B->cur = -1, B->launches = 0;
+        if (B->cur >= 0) P.chunk_tab = B->tab[B->cur];
+        const bool first = B->launches < B->measure_first;
+        if (first || (B->measure_every > 0 && B->launches % B->measure_every == 0)) {
+            const int nb = B->cur >= 0 ? 1 - B->cur : 0;
+            P.chunk_tab_next = B->tab[nb];
+            P.cta_ticks = B->ticks;
+            P.cta_done = B->done;
+            P.chunk_alpha = first ? 0.7f : 0.3f;
+            B->cur = nb;  // stream order: the next launch starts after this one has written it
+        }
+        B->launches += 1;
+    }
+    kern<<<grid, FUSED_TY, C::SMEM, stream>>>(P, nyt, chunk);
     return 0;
 }
 
 // the common row pitches get a kernel with Hp folded into the instruction immediates
 template <typename T>
-int launch_fused(const LbmParams<T> &P, cudaStream_t stream)
+int launch_fused(const LbmParams<T> &P, cudaStream_t stream, ChunkBalancer *B = nullptr)
 {
 #ifdef FDLBM_HP_SPECIALISATION  // measured on B200: no gain (19.88 vs 19.93 GLUPS), so off by default
     switch (P.Hp) {
-    case 2048: return launch_fused_hp<T, 2048>(P, stream);
-    case 4096: return launch_fused_hp<T, 4096>(P, stream);
-    case 8192: return launch_fused_hp<T, 8192>(P, stream);
+    case 2048: return launch_fused_hp<T, 2048>(P, stream, B);
+    case 4096: return launch_fused_hp<T, 4096>(P, stream, B);
+    case 8192: return launch_fused_hp<T, 8192>(P, stream, B);
     default: break;
     }
 #endif
-    return launch_fused_hp<T, 0>(P, stream);
+    return launch_fused_hp<T, 0>(P, stream, B);
 }
 
 }  // namespace fdlbm

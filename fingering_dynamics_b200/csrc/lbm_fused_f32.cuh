@@ -199,12 +199,10 @@ __global__ void __launch_bounds__(Cfg::NT, 3)
     constexpr unsigned FULL = 0xffffffffu;
     static_assert(D == 1 && NS == 4, "stage ring of four columns, one column ahead");
     static_assert(VecCfg<float, NT, 2>::SMEM == Cfg::SMEM && VecCfg<float, NT, 2>::ROWS == ROWS, "same strips as k_fused_vec");
-    const CtaTimer timer;
     if ((int)blockIdx.x >= n_fast) {  // face CTA
         const int k = (int)blockIdx.x - n_fast, side = k / nyt;
         const bool left = fx0 > 0 && side == 0;
         fused_vec_strip<float, NT, 2>(P, k % nyt, left ? 0 : fx1, left ? fx0 : P.Wl);
-        timer.stop(1000 + k % nyt);
         return;
     }
     extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -512,7 +510,6 @@ __global__ void __launch_bounds__(Cfg::NT, 3)
         fs_own += Hp >> 5, fs_edge += Hp >> 5;
     }
     cp_async_wait<0>();
-    timer.stop(yt);
 }
 
 // the plain column range of this slab: columns x with x and x+1 in the domain and away from the Zou-He faces

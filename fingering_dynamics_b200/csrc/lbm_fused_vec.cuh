@@ -327,18 +327,18 @@ namespace fdlbm {
 
 // the step kernel used for each storage type
 template <typename T>
-int launch_fused_auto(const LbmParams<T> &P, cudaStream_t stream);
+int launch_fused_auto(const LbmParams<T> &P, cudaStream_t stream, ChunkBalancer *B);
 template <>
-inline int launch_fused_auto<double>(const LbmParams<double> &P, cudaStream_t stream)
+inline int launch_fused_auto<double>(const LbmParams<double> &P, cudaStream_t stream, ChunkBalancer *B)
 {
 #ifdef FDLBM_F64_VEC1
     return launch_fused_vec<double, FUSED_TY, 1>(P, stream);
 #else
-    return launch_fused<double>(P, stream);
+    return launch_fused<double>(P, stream, B);
 #endif
 }
 template <>
-inline int launch_fused_auto<float>(const LbmParams<float> &P, cudaStream_t stream)
+inline int launch_fused_auto<float>(const LbmParams<float> &P, cudaStream_t stream, ChunkBalancer *B)
 {
 #if FDLBM_F32_VEC == 2
     // even heights: packed two-row kernel (lbm_fused_f32.cuh); FDLBM_F32_KERNEL=vec selects the scalar two-row kernel
@@ -349,7 +349,7 @@ inline int launch_fused_auto<float>(const LbmParams<float> &P, cudaStream_t stre
     if (!force_vec && f32p::applicable(P)) return f32p::launch(P, stream);
     return launch_fused_vec<float, FUSED_TY, 2>(P, stream);
 #else
-    return launch_fused<float>(P, stream);
+    return launch_fused<float>(P, stream, B);
 #endif
 }
 

@@ -82,6 +82,14 @@ class Compute(ComputeBase):
         self.feq, self.geq = feq, geq
         self.f, self.g = feq.copy(), geq.copy()
 
+    def _fields(self, **extra):
+        # validation.py keeps no gradient arrays up to date: getLarge_F evaluates getNabla_psix/psiy of the CURRENT psi
+        # itself (validation.py:174-190), so the collision operators get fresh gradients, not the attributes
+        gx, gy, _ = self._stencils()
+        extra.setdefault("nabla_psix", gx)
+        extra.setdefault("nabla_psiy", gy)
+        return super()._fields(**extra)
+
     def power_law(self, temp2):
         return power_law(self, temp2)
 

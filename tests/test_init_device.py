@@ -138,7 +138,7 @@ def test_device_init_on_peer_slabs_equals_the_single_slab_run():
 def test_init_and_window_argument_errors():
     from fingering_dynamics_b200 import Engine, synthetic as syn
     from fingering_dynamics_b200._native import FdlbmError
-    H, W = 64, 96
+    H, W = 128, 96
     c = syn.fp_constants(H)
     solid, refl = syn.porous_geometry(H, W)
     kw = dict(tau=c["tau"], gamma=c["gamma"], a=c["a"], kappa=c["kappa"], Eta_n=c["Eta_n"], M=c["M"], psi_wall=c["psi_wall"],
