@@ -559,19 +559,19 @@ int fdlbm_create(const fdlbm_config *cfg, fdlbm_engine **out)
         CUE(cudaMemsetAsync(e->psi[k], 0, e->plane_elems() * e->esize, e->stream));
     }
     {
-        // balancer buffers: two boundary tables, per-CTA durations, the completion counter
+        // balancer buffers: two boundary tables, per-CTA start / end / SM id, the completion counter
         ChunkBalancer &B = e->balancer;
-        const size_t n = 2 * ChunkBalancer::CAP_TAB + ChunkBalancer::CAP_CTA + 64;
+        const size_t n = 2 * ChunkBalancer::CAP_TAB + 3 * ChunkBalancer::CAP_CTA + 64;
         CUE(cudaMalloc((void **)&B.tab[0], n * sizeof(int)));
         CUE(cudaMemsetAsync(B.tab[0], 0, n * sizeof(int), e->stream));
         B.tab[1] = B.tab[0] + ChunkBalancer::CAP_TAB;
         B.ticks = (unsigned *)(B.tab[1] + ChunkBalancer::CAP_TAB);
-        B.done = B.ticks + ChunkBalancer::CAP_CTA;
+        B.done = B.ticks + 3 * ChunkBalancer::CAP_CTA;
         auto env_int = [](const char *name, int dflt) {
             const char *v = getenv(name);
             return v && *v ? atoi(v) : dflt;
         };
-        B.enabled = env_int("FDLBM_BALANCE", 1) != 0;
+        B.enabled = env_int("FDLBM_BALANCE", 0) != 0;  // measured -5 % on B200 (profiles/README.md): off unless asked for
         B.measure_first = env_int("FDLBM_BALANCE_FIRST", B.measure_first);
         B.measure_every = env_int("FDLBM_BALANCE_EVERY", B.measure_every);
     }
@@ -889,7 +889,8 @@ int fdlbm_peer_attach(fdlbm_engine *e, int side, const fdlbm_peer_info *nb)
     return 0;
 }
 
-int fdlbm_balance_info(fdlbm_engine *e, int32_t *nyt, int32_t *nchunks, int32_t *bounds, uint32_t *ticks_ns, int cap)
+int fdlbm_balance_info(fdlbm_engine *e, int32_t *nyt, int32_t *nchunks, int32_t *bounds, uint32_t *ticks_ns, uint32_t *sm_ids,
+                       int cap)
 {
     if (!e || !nyt || !nchunks) return fail(FDLBM_E_ARG, "null argument");
     CU(cudaSetDevice(e->cfg.device));
@@ -903,9 +904,16 @@ int fdlbm_balance_info(fdlbm_engine *e, int32_t *nyt, int32_t *nchunks, int32_t 
         if (cap < ntab) return fail(FDLBM_E_ARG, "bounds needs %d entries", ntab);
         CU(cudaMemcpy(bounds, B.tab[B.cur], (size_t)ntab * sizeof(int), cudaMemcpyDeviceToHost));
     }
-    if (ticks_ns) {
+    if (ticks_ns) {  // end - start of every CTA of the last measuring launch
         if (cap < B.grid) return fail(FDLBM_E_ARG, "ticks_ns needs %d entries", B.grid);
-        CU(cudaMemcpy(ticks_ns, B.ticks, (size_t)B.grid * sizeof(unsigned), cudaMemcpyDeviceToHost));
+        std::vector<uint32_t> t0(B.grid), t1(B.grid);
+        CU(cudaMemcpy(t0.data(), B.ticks, (size_t)B.grid * sizeof(unsigned), cudaMemcpyDeviceToHost));
+        CU(cudaMemcpy(t1.data(), B.ticks + ChunkBalancer::CAP_CTA, (size_t)B.grid * sizeof(unsigned), cudaMemcpyDeviceToHost));
+        for (int i = 0; i < B.grid; ++i) ticks_ns[i] = t1[i] - t0[i];
+    }
+    if (sm_ids) {
+        if (cap < B.grid) return fail(FDLBM_E_ARG, "sm_ids needs %d entries", B.grid);
+        CU(cudaMemcpy(sm_ids, B.ticks + 2 * ChunkBalancer::CAP_CTA, (size_t)B.grid * sizeof(unsigned), cudaMemcpyDeviceToHost));
     }
     return 0;
 }

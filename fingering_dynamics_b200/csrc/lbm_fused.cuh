@@ -171,32 +171,68 @@ __device__ __forceinline__ void pull_staged(const T *sm, const T *s0, const T *s
 }
 
 // ---- balancer ------------------------------------------------------------------------------------------------
-// One resident wave ends with its slowest CTA, and the spread between CTAs is systematic: a few SMs run ~5 % slower
+// One resident wave ends with its slowest SM, and the spread between SMs is systematic: a few SMs run ~5 % slower
 // than the rest, and SMs that were handed two CTAs instead of three finish far ahead.  A MEASURING launch records
-// the duration of every CTA (%globaltimer); the CTA that finishes last turns them into new column boundaries for the
-// NEXT launch, strip by strip: each chunk's length moves towards Wl * v_c / sum(v) with v_c = columns / duration of
-// the CTA that had chunk c (CTA -> SM placement of a one-wave grid repeats from launch to launch).  Nothing is added
-// to the column loop, and results do not depend on the boundaries (every cell is computed by exactly one CTA with the
-// same arithmetic whatever its range).
+// start, end (%globaltimer) and %smid of every CTA; the CTA that finishes last turns them into new column boundaries
+// for the NEXT launch.  The unit is the SM, not the CTA: the CTAs of one SM share its throughput (an early finisher
+// hands its share to the others), so v_sm = columns of all its CTAs / time until the last of them finished, and every
+// CTA of that SM is given the same share v_sm / n_sm of its strip (per-CTA feedback was measured and LOSES 5 %: it
+// equalises the first / second / third CTA of an SM, which changes nothing for the SM, and pulls the strips of a
+// chunk out of lock step).  CTA -> SM placement of a one-wave grid repeats from launch to launch; if it ever does
+// not, the boundaries are merely not optimal: results do not depend on them (every cell is computed by exactly one
+// CTA with the same arithmetic whatever its range).  Nothing is added to the column loop.
 __device__ __forceinline__ unsigned long long global_ns()
 {
     unsigned long long t;
     asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
     return t;
 }
-
-template <typename T, int TY>
-__device__ __noinline__ void rebalance_chunks(const LbmParams<T> &P, int nyt, int chunk)
+__device__ __forceinline__ unsigned sm_id()
 {
-    const int nch = (int)gridDim.x / nyt, Wl = P.Wl;
+    unsigned s;
+    asm volatile("mov.u32 %0, %%smid;" : "=r"(s));
+    return s;
+}
+constexpr int BAL_CAP_CTA = 2048, BAL_CAP_TAB = 4096, BAL_MAX_SM = 512;
+
+// `scratch`: >= 4 * BAL_MAX_SM ints of shared memory (the g stages, no longer in use)
+template <typename T, int TY>
+__device__ __noinline__ void rebalance_chunks(const LbmParams<T> &P, int nyt, int chunk, int *scratch)
+{
+    const int grid = (int)gridDim.x, nch = grid / nyt, Wl = P.Wl;
     const int minlen = min(8, Wl / nch);
+    const unsigned *t_beg = P.cta_ticks, *t_end = P.cta_ticks + BAL_CAP_CTA, *smid = P.cta_ticks + 2 * BAL_CAP_CTA;
+    int *sm_len = scratch, *sm_n = scratch + BAL_MAX_SM, *sm_t0 = scratch + 2 * BAL_MAX_SM, *sm_t1 = scratch + 3 * BAL_MAX_SM;
+    float *sm_v = reinterpret_cast<float *>(sm_len);  // overwrites sm_len once the sums are complete
+    auto len_of = [&](int cta) {
+        const int s = cta % nyt, c = cta / nyt;
+        if (P.chunk_tab) return P.chunk_tab[(size_t)s * (nch + 1) + c + 1] - P.chunk_tab[(size_t)s * (nch + 1) + c];
+        return min(Wl, (c + 1) * chunk) - c * chunk;
+    };
+    for (int s = threadIdx.x; s < BAL_MAX_SM; s += TY) sm_len[s] = 0, sm_n[s] = 0, sm_t0[s] = 0x7fffffff, sm_t1[s] = -0x7fffffff;
+    __syncthreads();
+    const unsigned ref = __ldcg(t_beg);  // times relative to the start of CTA 0 (32-bit ns differences)
+    for (int i = threadIdx.x; i < grid; i += TY) {
+        const unsigned s = __ldcg(smid + i);
+        if (s < (unsigned)BAL_MAX_SM) {
+            atomicAdd(&sm_len[s], len_of(i));
+            atomicAdd(&sm_n[s], 1);
+            atomicMin(&sm_t0[s], (int)(__ldcg(t_beg + i) - ref));
+            atomicMax(&sm_t1[s], (int)(__ldcg(t_end + i) - ref));
+        }
+    }
+    __syncthreads();
+    for (int s = threadIdx.x; s < BAL_MAX_SM; s += TY) {
+        const int n = sm_n[s], L = sm_len[s], dt = sm_t1[s] - sm_t0[s];
+        sm_v[s] = n > 0 && dt > 0 ? (float)L / ((float)dt * (float)n) : 0.f;  // share of one CTA of this SM
+    }
+    __syncthreads();
     for (int s = threadIdx.x; s < nyt; s += TY) {
-        const int *cur = P.chunk_tab ? P.chunk_tab + (size_t)s * (nch + 1) : nullptr;
         int *nxt = P.chunk_tab_next + (size_t)s * (nch + 1);
-        auto len_of = [&](int c) { return cur ? cur[c + 1] - cur[c] : min(Wl, (c + 1) * chunk) - c * chunk; };
         auto speed = [&](int c) {
-            const unsigned d = __ldcg(P.cta_ticks + (size_t)c * nyt + s);
-            return (float)len_of(c) / (float)(d > 0u ? d : 1u);
+            const unsigned sm = __ldcg(smid + c * nyt + s);
+            const float v = sm < (unsigned)BAL_MAX_SM ? sm_v[sm] : 0.f;
+            return v > 0.f ? v : 1e-3f;
         };
         float vsum = 0.f;
         for (int c = 0; c < nch; ++c) vsum += speed(c);
@@ -204,7 +240,7 @@ __device__ __noinline__ void rebalance_chunks(const LbmParams<T> &P, int nyt, in
         int prev = 0;
         nxt[0] = 0;
         for (int c = 0; c < nch - 1; ++c) {
-            const float len = (float)len_of(c);
+            const float len = (float)len_of(c * nyt + s);
             acc += len + P.chunk_alpha * ((float)Wl * speed(c) / vsum - len);
             int b = (int)(acc + 0.5f);
             b = max(b, prev + minlen);
@@ -454,14 +490,16 @@ __global__ void __launch_bounds__(TY, sizeof(T) == 8 ? FDLBM_FUSED_MINB64 : FDLB
     if (P.chunk_tab_next) {  // measuring launch (CTA-uniform)
         __syncthreads();
         if (t == 0) {
-            P.cta_ticks[blockIdx.x] = (unsigned)(global_ns() - s_t0);
+            P.cta_ticks[blockIdx.x] = (unsigned)s_t0;
+            P.cta_ticks[BAL_CAP_CTA + blockIdx.x] = (unsigned)global_ns();
+            P.cta_ticks[2 * BAL_CAP_CTA + blockIdx.x] = sm_id();
             __threadfence();
             s_last = atomicAdd(P.cta_done, 1u) == gridDim.x - 1;
         }
         __syncthreads();
         if (s_last) {
             __threadfence();
-            rebalance_chunks<T, TY>(P, nyt, chunk);
+            rebalance_chunks<T, TY>(P, nyt, chunk, reinterpret_cast<int *>(smem_raw));
             if (t == 0) *P.cta_done = 0u;
         }
     }
@@ -491,15 +529,15 @@ inline int fused_chunk(int nyt, int n_cta, int Wl)
 
 // host side of the balancer: device buffers owned by the engine + what the next launch should do
 struct ChunkBalancer {
-    static constexpr int CAP_CTA = 2048, CAP_TAB = 4096;
+    static constexpr int CAP_CTA = BAL_CAP_CTA, CAP_TAB = BAL_CAP_TAB;
     int *tab[2] = {nullptr, nullptr};  // boundary tables, read / written alternately
-    unsigned *ticks = nullptr, *done = nullptr;
+    unsigned *ticks = nullptr, *done = nullptr;  // ticks: [3][CAP_CTA] start, end (low 32 bits of ns), %smid
     bool enabled = false;
     int cur = -1;                      // table holding valid boundaries, -1: none yet (equal chunks)
     int grid = 0, nyt = 0;             // launch shape the boundaries belong to
     long launches = 0;                 // fused launches of that shape so far
-    int measure_first = 12;            // every one of the first launches measures and rebalances (damping 0.7) ...
-    int measure_every = 64;            // ... then one in so many (damping 0.3); 0: never again
+    int measure_first = 8;             // every one of the first launches measures and rebalances (damping 0.5) ...
+    int measure_every = 64;            // ... then one in so many (damping 0.25); 0: never again
 };
 
 // returns 0 or a cudaError_t
@@ -543,7 +581,7 @@ int launch_fused_hp(const LbmParams<T> &P_, cudaStream_t stream, ChunkBalancer *
             P.chunk_tab_next = B->tab[nb];
             P.cta_ticks = B->ticks;
             P.cta_done = B->done;
-            P.chunk_alpha = first ? 0.7f : 0.3f;
+            P.chunk_alpha = first ? 0.5f : 0.25f;
             B->cur = nb;  // stream order: the next launch starts after this one has written it
         }
         B->launches += 1;

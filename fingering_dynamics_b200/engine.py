@@ -184,18 +184,21 @@ class Engine:
             raise FloatingPointError("%d non-finite populations after %d iterations" % (n, self.iterations))
 
     def balance_info(self):
-        """chunk balancer of the fused fp64 step: {'nyt', 'nchunks', 'bounds' (nyt, nchunks+1), 'ticks_ns' (nchunks, nyt)};
-        bounds is None while the chunks are still equal"""
+        """chunk balancer of the fused fp64 step: {'nyt', 'nchunks', 'bounds' (nyt, nchunks+1), 'ticks_ns' (nchunks, nyt),
+        'sm_ids' (nchunks, nyt)}; bounds is None while the chunks are still equal"""
         nyt, nch = ctypes.c_int32(0), ctypes.c_int32(0)
-        nat.check(nat.lib().fdlbm_balance_info(self._h, ctypes.byref(nyt), ctypes.byref(nch), None, None, 0))
-        out = {"nyt": nyt.value, "nchunks": nch.value, "bounds": None, "ticks_ns": None}
+        nat.check(nat.lib().fdlbm_balance_info(self._h, ctypes.byref(nyt), ctypes.byref(nch), None, None, None, 0))
+        out = {"nyt": nyt.value, "nchunks": nch.value, "bounds": None, "ticks_ns": None, "sm_ids": None}
         if nyt.value > 0 and nch.value > 0:
             b = np.full(nyt.value * (nch.value + 1), -1, dtype=np.int32)
             t = np.zeros(nyt.value * nch.value, dtype=np.uint32)
-            nat.check(nat.lib().fdlbm_balance_info(self._h, ctypes.byref(nyt), ctypes.byref(nch), nat.ptr(b), nat.ptr(t), b.size))
+            s = np.zeros(nyt.value * nch.value, dtype=np.uint32)
+            nat.check(nat.lib().fdlbm_balance_info(self._h, ctypes.byref(nyt), ctypes.byref(nch), nat.ptr(b), nat.ptr(t),
+                                                   nat.ptr(s), b.size))
             if b[0] >= 0:
                 out["bounds"] = b.reshape(nyt.value, nch.value + 1)
                 out["ticks_ns"] = t.reshape(nch.value, nyt.value)
+                out["sm_ids"] = s.reshape(nch.value, nyt.value)
         return out
 
     def peer_export(self):

@@ -180,9 +180,11 @@ int fdlbm_peer_attach(fdlbm_engine *e, int side, const fdlbm_peer_info *nb);
 
 /* Diagnostics of the fused fp64 step's chunk balancer (csrc/lbm_fused.cuh; no counterpart in the reference): the
  * launch shape (strips x column chunks per strip), the column boundaries in use ([strip][chunk + 1], untouched while
- * the chunks are still equal) and the CTA durations in ns of the last measuring launch ([chunk * nyt + strip]).
- * `cap` = entries each non-NULL array has room for.  FDLBM_BALANCE=0 in the environment switches the balancer off. */
-int fdlbm_balance_info(fdlbm_engine *e, int32_t *nyt, int32_t *nchunks, int32_t *bounds, uint32_t *ticks_ns, int cap);
+ * the chunks are still equal), and of the last measuring launch the CTA durations in ns and the SM each CTA ran on
+ * (both [chunk * nyt + strip]).  `cap` = entries each non-NULL array has room for.  FDLBM_BALANCE=0/1 in the
+ * environment switches the balancer off / on. */
+int fdlbm_balance_info(fdlbm_engine *e, int32_t *nyt, int32_t *nchunks, int32_t *bounds, uint32_t *ticks_ns, uint32_t *sm_ids,
+                       int cap);
 
 /* page-locked host memory for the e2e path */
 void *fdlbm_pinned_alloc(size_t bytes);
