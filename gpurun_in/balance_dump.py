@@ -30,6 +30,19 @@ for upto in (1, 2, 3, 4, 6, 8, 12, 13, 40, 200):
         s["ticks_us"] = {"min": t.min() / 1e3, "mean": t.mean() / 1e3, "max": t.max() / 1e3, "p5": float(np.percentile(t, 5)) / 1e3,
                          "p95": float(np.percentile(t, 95)) / 1e3}
         s["ticks_by_chunk_us_mean"] = (t.mean(axis=1) / 1e3).round(1).tolist()
+        sm = bi["sm_ids"]
+        lens = np.diff(bi["bounds"], axis=1).T          # (nchunks, nyt) like ticks / sm_ids
+        per = {}
+        for k in np.unique(sm):
+            sel = sm == k
+            per[int(k)] = [int(sel.sum()), int(lens[sel].sum()), float(t[sel].max() / 1e3)]
+        full = [v for v in per.values() if v[0] == 3]
+        s["sms"] = len(per)
+        s["sm_ctas_hist"] = {str(n): sum(1 for v in per.values() if v[0] == n) for n in (1, 2, 3, 4)}
+        s["sm_slowest_cta_us"] = {"min": min(v[2] for v in per.values()), "median": float(np.median([v[2] for v in per.values()])),
+                                  "max": max(v[2] for v in per.values())}
+        if done in (2, 13, 200):
+            s["per_sm"] = per
     out["snap"].append(s)
 win = []
 for _ in range(8):
