@@ -68,7 +68,7 @@ struct fdlbm_engine {
     int peer_Wl[2] = {0, 0};
     bool peer_ipc[2] = {false, false};
     uint32_t peer_step = 0;                                   // steps taken in peer mode (never reset)
-    ChunkBalancer balancer;                                   // measured column chunks of the fused step (lbm_fused.cuh)
+    Placement placement;                                      // CTA placement of the fused fp64 step (lbm_fused.cuh)
     int cur = 0, pcur = 0;
     int state = ST_EMPTY;
     bool have_geometry = false;
@@ -118,11 +118,8 @@ LbmParams<T> make_params(const fdlbm_engine *e, int src, int psrc)
     P.f3coef = (T)c.outlet_f3_coef;
     P.peer_lo = P.peer_hi = nullptr;
     P.peer_lo_Wl = 0;
-    P.chunk_tab = nullptr;
-    P.chunk_tab_next = nullptr;
-    P.cta_ticks = nullptr;
-    P.cta_done = nullptr;
-    P.chunk_alpha = 0.f;
+    P.place = nullptr;
+    P.place_mode = P.place_items = P.place_mark = 0;
     return P;
 }
 
@@ -248,7 +245,7 @@ int launch_step(fdlbm_engine *e, bool finalize)
             k_step_twopass<T, false><<<cell_grid(e, e->Wl), TPB, 0, e->stream>>>(P, field_ptrs<T>(e));
         e->launches += 2;
     } else {
-        int rc = launch_fused_auto<T>(P, e->stream, &e->balancer);
+        int rc = launch_fused_auto<T>(P, e->stream, &e->placement);
         if (rc) return fail(FDLBM_E_CUDA, "fused launch configuration failed (%d)", rc);
         e->launches += 1;
     }
@@ -559,21 +556,16 @@ int fdlbm_create(const fdlbm_config *cfg, fdlbm_engine **out)
         CUE(cudaMemsetAsync(e->psi[k], 0, e->plane_elems() * e->esize, e->stream));
     }
     {
-        // balancer buffers: two boundary tables, per-CTA start / end / SM id, the completion counter
-        ChunkBalancer &B = e->balancer;
-        const size_t n = 2 * ChunkBalancer::CAP_TAB + 3 * ChunkBalancer::CAP_CTA + 64;
-        CUE(cudaMalloc((void **)&B.tab[0], n * sizeof(int)));
-        CUE(cudaMemsetAsync(B.tab[0], 0, n * sizeof(int), e->stream));
-        B.tab[1] = B.tab[0] + ChunkBalancer::CAP_TAB;
-        B.ticks = (unsigned *)(B.tab[1] + ChunkBalancer::CAP_TAB);
-        B.done = B.ticks + 3 * ChunkBalancer::CAP_CTA;
+        Placement &B = e->placement;
+        CUE(cudaMalloc((void **)&B.buf, PlaceBuf::SIZE * sizeof(int)));
+        CUE(cudaMemsetAsync(B.buf, 0, PlaceBuf::SIZE * sizeof(int), e->stream));
         auto env_int = [](const char *name, int dflt) {
             const char *v = getenv(name);
             return v && *v ? atoi(v) : dflt;
         };
-        B.enabled = env_int("FDLBM_BALANCE", 0) != 0;  // measured -5 % on B200 (profiles/README.md): off unless asked for
-        B.measure_first = env_int("FDLBM_BALANCE_FIRST", B.measure_first);
-        B.measure_every = env_int("FDLBM_BALANCE_EVERY", B.measure_every);
+        B.enabled = env_int("FDLBM_PLACEMENT", 1) != 0;
+        B.measure_n = env_int("FDLBM_PLACEMENT_MEASURE", B.measure_n);
+        if (B.measure_n < 1) B.measure_n = 1;
     }
     CUE(cudaMalloc((void **)&e->flags, 256));
     CUE(cudaMemsetAsync(e->flags, 0, 256, e->stream));
@@ -615,7 +607,7 @@ void fdlbm_destroy(fdlbm_engine *e)
             cudaIpcCloseMemHandle(e->peer_flags[side]);
         }
     void *ptrs[] = {e->lat[0], e->lat[1], e->psi[0], e->psi[1], e->fields, e->reflect, e->solid_bytes,
-                    e->solid, e->inlet, e->outlet, e->staging, e->flags, e->balancer.tab[0]};
+                    e->solid, e->inlet, e->outlet, e->staging, e->flags, e->placement.buf};
     for (void *p : ptrs)
         if (p) cudaFree(p);
     if (e->stream) cudaStreamDestroy(e->stream);
@@ -889,31 +881,33 @@ int fdlbm_peer_attach(fdlbm_engine *e, int side, const fdlbm_peer_info *nb)
     return 0;
 }
 
-int fdlbm_balance_info(fdlbm_engine *e, int32_t *nyt, int32_t *nchunks, int32_t *bounds, uint32_t *ticks_ns, uint32_t *sm_ids,
-                       int cap)
+int fdlbm_placement_info(fdlbm_engine *e, int32_t *items, int32_t *n_marked, int32_t *marked_sms, uint32_t *ticks_ns,
+                         uint32_t *sm_ids, int cap)
 {
-    if (!e || !nyt || !nchunks) return fail(FDLBM_E_ARG, "null argument");
+    if (!e || !items || !n_marked) return fail(FDLBM_E_ARG, "null argument");
     CU(cudaSetDevice(e->cfg.device));
     CU(cudaStreamSynchronize(e->stream));
-    const ChunkBalancer &B = e->balancer;
-    *nyt = B.nyt;
-    *nchunks = B.nyt > 0 ? B.grid / B.nyt : 0;
-    if (B.cur < 0 || B.nyt <= 0) return 0;  // equal chunks so far
-    const int ntab = B.nyt * (*nchunks + 1);
-    if (bounds) {
-        if (cap < ntab) return fail(FDLBM_E_ARG, "bounds needs %d entries", ntab);
-        CU(cudaMemcpy(bounds, B.tab[B.cur], (size_t)ntab * sizeof(int), cudaMemcpyDeviceToHost));
+    const Placement &B = e->placement;
+    *items = B.items;
+    *n_marked = B.marked ? B.n_skip : 0;
+    if (!B.buf || B.items <= 0) return 0;
+    if (marked_sms && B.marked) {
+        if (cap < B.n_skip) return fail(FDLBM_E_ARG, "marked_sms needs %d entries", B.n_skip);
+        std::vector<int> skip(PlaceBuf::MAX_SM);
+        CU(cudaMemcpy(skip.data(), B.buf + PlaceBuf::SKIP, skip.size() * sizeof(int), cudaMemcpyDeviceToHost));
+        int n = 0;
+        for (int s = 0; s < PlaceBuf::MAX_SM && n < B.n_skip; ++s)
+            if (skip[s]) marked_sms[n++] = s;
+        *n_marked = n;
     }
-    if (ticks_ns) {  // end - start of every CTA of the last measuring launch
-        if (cap < B.grid) return fail(FDLBM_E_ARG, "ticks_ns needs %d entries", B.grid);
-        std::vector<uint32_t> t0(B.grid), t1(B.grid);
-        CU(cudaMemcpy(t0.data(), B.ticks, (size_t)B.grid * sizeof(unsigned), cudaMemcpyDeviceToHost));
-        CU(cudaMemcpy(t1.data(), B.ticks + ChunkBalancer::CAP_CTA, (size_t)B.grid * sizeof(unsigned), cudaMemcpyDeviceToHost));
-        for (int i = 0; i < B.grid; ++i) ticks_ns[i] = t1[i] - t0[i];
-    }
-    if (sm_ids) {
-        if (cap < B.grid) return fail(FDLBM_E_ARG, "sm_ids needs %d entries", B.grid);
-        CU(cudaMemcpy(sm_ids, B.ticks + 2 * ChunkBalancer::CAP_CTA, (size_t)B.grid * sizeof(unsigned), cudaMemcpyDeviceToHost));
+    if (ticks_ns || sm_ids) {  // of the last measuring launch (grid = items)
+        if (cap < B.items) return fail(FDLBM_E_ARG, "ticks_ns / sm_ids need %d entries", B.items);
+        std::vector<uint32_t> t0(B.items), t1(B.items);
+        CU(cudaMemcpy(t0.data(), B.buf + PlaceBuf::T_BEG, (size_t)B.items * sizeof(int), cudaMemcpyDeviceToHost));
+        CU(cudaMemcpy(t1.data(), B.buf + PlaceBuf::T_END, (size_t)B.items * sizeof(int), cudaMemcpyDeviceToHost));
+        if (ticks_ns)
+            for (int i = 0; i < B.items; ++i) ticks_ns[i] = t1[i] - t0[i];
+        if (sm_ids) CU(cudaMemcpy(sm_ids, B.buf + PlaceBuf::SMID, (size_t)B.items * sizeof(int), cudaMemcpyDeviceToHost));
     }
     return 0;
 }

@@ -37,14 +37,12 @@ struct LbmParams {
     // two edge columns straight into their ghost columns (halo exchange fused into the step)
     T *peer_lo, *peer_hi;
     int peer_lo_Wl;           // owned columns of the low-side neighbour (its high ghosts are columns Wl, Wl+1)
-    // measured column chunks of the fused fp64 step (lbm_fused.cuh, "balancer"): boundaries this launch uses
-    // ([strip][chunk + 1], nullptr = equal chunks) and, on a measuring launch, where the CTA that finishes last
-    // writes the boundaries for the next launch from the CTA durations of this one
-    const int *chunk_tab;
-    int *chunk_tab_next;
-    unsigned *cta_ticks;      // [CTA] duration in ns of each CTA of a measuring launch
-    unsigned *cta_done;       // CTAs finished so far (reset by the last one)
-    float chunk_alpha;        // damping of a rebalancing step
+    // CTA placement of the fused fp64 step (lbm_fused.cuh, "placement"): nullptr = CTA i works on item i
+    int *place;               // device block, layout PlaceBuf
+    int place_mode;           // 1: measuring launch (plain mapping, records start / end / %smid per CTA),
+                              // 2: work items are taken by ticket and the SMs marked slow host one CTA less
+    int place_items;          // work items of this launch (strips x column chunks)
+    int place_mark;           // measuring launch: > 0 = mark this many SMs slow once the launch is over
 };
 
 // macroscopic outputs of the finalize pass / inputs of the first collision, each [(xl+G)*Hp + y]

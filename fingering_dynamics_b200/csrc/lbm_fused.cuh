@@ -170,17 +170,18 @@ __device__ __forceinline__ void pull_staged(const T *sm, const T *s0, const T *s
     v[8] = *s8;
 }
 
-// ---- balancer ------------------------------------------------------------------------------------------------
-// One resident wave ends with its slowest SM, and the spread between SMs is systematic: a few SMs run ~5 % slower
-// than the rest, and SMs that were handed two CTAs instead of three finish far ahead.  A MEASURING launch records
-// start, end (%globaltimer) and %smid of every CTA; the CTA that finishes last turns them into new column boundaries
-// for the NEXT launch.  The unit is the SM, not the CTA: the CTAs of one SM share its throughput (an early finisher
-// hands its share to the others), so v_sm = columns of all its CTAs / time until the last of them finished, and every
-// CTA of that SM is given the same share v_sm / n_sm of its strip (per-CTA feedback was measured and LOSES 5 %: it
-// equalises the first / second / third CTA of an SM, which changes nothing for the SM, and pulls the strips of a
-// chunk out of lock step).  CTA -> SM placement of a one-wave grid repeats from launch to launch; if it ever does
-// not, the boundaries are merely not optimal: results do not depend on them (every cell is computed by exactly one
-// CTA with the same arithmetic whatever its range).  Nothing is added to the column loop.
+// ---- placement ---------------------------------------------------------------------------------------------
+// One resident wave ends with its slowest SM, and the spread between SMs is systematic: on B200 a handful of SMs
+// (ids 0, 1, 142-147 on every box measured) need ~5 % longer for the same three CTAs, and the one-wave grid leaves a
+// few CTA slots empty anyway (8192x2048: 432 work items on 444 slots), which the hardware hands to whatever SMs come
+// last in its order.  Two attempts to even this out by moving the column boundaries (per CTA, then per SM) were
+// measured and LOSE 5 % (profiles/README.md): chunks of unequal length pull the strips of a chunk out of lock step,
+// their apron rows stop being L2 hits and the whole machine slows down.  So the chunks stay equal and only the
+// PLACEMENT changes: measuring launches record start / end / %smid of every CTA; the CTA that finishes last adds up
+// the time each SM needed; after the last measuring launch the (slots - items) slowest SMs are marked.  From then
+// on the grid fills every slot, the first CTA to arrive on a marked SM exits at once, and the others take their
+// work item by ticket (strips stay the fast index, so the CTAs of a chunk still start together).  Results do not
+// depend on any of this: every item is worked on by exactly one CTA with the same arithmetic.
 __device__ __forceinline__ unsigned long long global_ns()
 {
     unsigned long long t;
@@ -193,61 +194,75 @@ __device__ __forceinline__ unsigned sm_id()
     asm volatile("mov.u32 %0, %%smid;" : "=r"(s));
     return s;
 }
-constexpr int BAL_CAP_CTA = 2048, BAL_CAP_TAB = 4096, BAL_MAX_SM = 512;
+struct PlaceBuf {  // offsets (ints) into LbmParams::place
+    static constexpr int MAX_SM = 512, CAP_CTA = 2048;
+    static constexpr int TICKET = 0, DONE = 1, MEASURED = 2;
+    static constexpr int SKIP = 16, CNT = SKIP + MAX_SM, ACC = CNT + MAX_SM;
+    static constexpr int T_BEG = ACC + MAX_SM, T_END = T_BEG + CAP_CTA, SMID = T_END + CAP_CTA, SIZE = SMID + CAP_CTA;
+};
 
-// `scratch`: >= 4 * BAL_MAX_SM ints of shared memory (the g stages, no longer in use)
-template <typename T, int TY>
-__device__ __noinline__ void rebalance_chunks(const LbmParams<T> &P, int nyt, int chunk, int *scratch)
+// measuring launch, CTA that finished last: time per SM of this launch added to ACC; optionally mark the slowest.
+// `scratch`: >= 3 * MAX_SM ints of shared memory (the g stages, no longer in use)
+template <int TY>
+__device__ __noinline__ void place_account(int *pb, int grid, int mark, int *scratch)
 {
-    const int grid = (int)gridDim.x, nch = grid / nyt, Wl = P.Wl;
-    const int minlen = min(8, Wl / nch);
-    const unsigned *t_beg = P.cta_ticks, *t_end = P.cta_ticks + BAL_CAP_CTA, *smid = P.cta_ticks + 2 * BAL_CAP_CTA;
-    int *sm_len = scratch, *sm_n = scratch + BAL_MAX_SM, *sm_t0 = scratch + 2 * BAL_MAX_SM, *sm_t1 = scratch + 3 * BAL_MAX_SM;
-    float *sm_v = reinterpret_cast<float *>(sm_len);  // overwrites sm_len once the sums are complete
-    auto len_of = [&](int cta) {
-        const int s = cta % nyt, c = cta / nyt;
-        if (P.chunk_tab) return P.chunk_tab[(size_t)s * (nch + 1) + c + 1] - P.chunk_tab[(size_t)s * (nch + 1) + c];
-        return min(Wl, (c + 1) * chunk) - c * chunk;
-    };
-    for (int s = threadIdx.x; s < BAL_MAX_SM; s += TY) sm_len[s] = 0, sm_n[s] = 0, sm_t0[s] = 0x7fffffff, sm_t1[s] = -0x7fffffff;
+    constexpr int MAX_SM = PlaceBuf::MAX_SM;
+    int *sm_n = scratch, *sm_t0 = scratch + MAX_SM, *sm_t1 = scratch + 2 * MAX_SM;
+    const unsigned *t_beg = (const unsigned *)pb + PlaceBuf::T_BEG, *t_end = (const unsigned *)pb + PlaceBuf::T_END;
+    const unsigned *smid = (const unsigned *)pb + PlaceBuf::SMID;
+    for (int s = threadIdx.x; s < MAX_SM; s += TY) sm_n[s] = 0, sm_t0[s] = 0x7fffffff, sm_t1[s] = -0x7fffffff;
     __syncthreads();
     const unsigned ref = __ldcg(t_beg);  // times relative to the start of CTA 0 (32-bit ns differences)
     for (int i = threadIdx.x; i < grid; i += TY) {
         const unsigned s = __ldcg(smid + i);
-        if (s < (unsigned)BAL_MAX_SM) {
-            atomicAdd(&sm_len[s], len_of(i));
+        if (s < (unsigned)MAX_SM) {
             atomicAdd(&sm_n[s], 1);
             atomicMin(&sm_t0[s], (int)(__ldcg(t_beg + i) - ref));
             atomicMax(&sm_t1[s], (int)(__ldcg(t_end + i) - ref));
         }
     }
     __syncthreads();
-    for (int s = threadIdx.x; s < BAL_MAX_SM; s += TY) {
-        const int n = sm_n[s], L = sm_len[s], dt = sm_t1[s] - sm_t0[s];
-        sm_v[s] = n > 0 && dt > 0 ? (float)L / ((float)dt * (float)n) : 0.f;  // share of one CTA of this SM
+    int nmax = 0;
+    for (int s = 0; s < MAX_SM; ++s) nmax = max(nmax, sm_n[s]);
+    for (int s = threadIdx.x; s < MAX_SM; s += TY) {
+        // only SMs that carried the full number of CTAs are comparable; the others count as fast
+        const int dt = sm_n[s] == nmax ? sm_t1[s] - sm_t0[s] : 0;
+        pb[PlaceBuf::ACC + s] += dt;
+        sm_t0[s] = pb[PlaceBuf::ACC + s];
     }
     __syncthreads();
-    for (int s = threadIdx.x; s < nyt; s += TY) {
-        int *nxt = P.chunk_tab_next + (size_t)s * (nch + 1);
-        auto speed = [&](int c) {
-            const unsigned sm = __ldcg(smid + c * nyt + s);
-            const float v = sm < (unsigned)BAL_MAX_SM ? sm_v[sm] : 0.f;
-            return v > 0.f ? v : 1e-3f;
-        };
-        float vsum = 0.f;
-        for (int c = 0; c < nch; ++c) vsum += speed(c);
-        float acc = 0.f;
-        int prev = 0;
-        nxt[0] = 0;
-        for (int c = 0; c < nch - 1; ++c) {
-            const float len = (float)len_of(c * nyt + s);
-            acc += len + P.chunk_alpha * ((float)Wl * speed(c) / vsum - len);
-            int b = (int)(acc + 0.5f);
-            b = max(b, prev + minlen);
-            b = min(b, Wl - (nch - 1 - c) * minlen);
-            nxt[c + 1] = prev = b;
+    if (mark > 0)
+        for (int s = threadIdx.x; s < MAX_SM; s += TY) {
+            const int mine = sm_t0[s];
+            int rank = 0;
+            for (int o = 0; o < MAX_SM; ++o) rank += (sm_t0[o] > mine) || (sm_t0[o] == mine && o < s);
+            pb[PlaceBuf::SKIP + s] = (mine > 0 && rank < mark) ? 1 : 0;
         }
-        nxt[nch] = Wl;
+}
+
+// end of every CTA of a launch with placement (also of the CTAs that exit without work)
+template <int TY>
+__device__ __forceinline__ void place_epilogue(int *pb, int mode, int mark, unsigned long long t0, int *scratch, int *s_last)
+{
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        if (mode == 1) {
+            pb[PlaceBuf::T_BEG + blockIdx.x] = (int)(unsigned)t0;
+            pb[PlaceBuf::T_END + blockIdx.x] = (int)(unsigned)global_ns();
+            pb[PlaceBuf::SMID + blockIdx.x] = (int)sm_id();
+        }
+        __threadfence();
+        *s_last = atomicAdd(pb + PlaceBuf::DONE, 1) == (int)gridDim.x - 1;
+    }
+    __syncthreads();
+    if (*s_last) {  // everybody else is done: account / reset for the next launch
+        __threadfence();
+        if (mode == 1) {
+            place_account<TY>(pb, (int)gridDim.x, mark, scratch);
+        } else {
+            for (int s = threadIdx.x; s < PlaceBuf::MAX_SM; s += TY) pb[PlaceBuf::CNT + s] = 0;
+        }
+        if (threadIdx.x == 0) pb[PlaceBuf::TICKET] = 0, pb[PlaceBuf::DONE] = 0, pb[PlaceBuf::MEASURED] += mode == 1;
     }
 }
 
@@ -266,22 +281,39 @@ __global__ void __launch_bounds__(TY, sizeof(T) == 8 ? FDLBM_FUSED_MINB64 : FDLB
     extern __shared__ __align__(16) unsigned char smem_raw[];
     T *gst = reinterpret_cast<T *>(smem_raw);        // [NS][9][PT]
     __shared__ __align__(8) unsigned long long bars[NS];  // one mbarrier per g stage (bulk-copy path)
-    __shared__ unsigned long long s_t0;                   // balancer: start time of this CTA
-    __shared__ int s_last;
+    __shared__ unsigned long long s_t0;                   // placement: start time of this CTA (measuring launch)
+    __shared__ int s_last, s_item;
     const int t = threadIdx.x, lane = t & 31;
-    if (P.chunk_tab_next && t == 0) s_t0 = global_ns();
+    // work item of this CTA: its block index, or -- once the engine has marked the slow SMs -- a ticket
+    int item = blockIdx.x;
+    if (P.place) {  // CTA-uniform
+        if (t == 0) {
+            if (P.place_mode == 1) s_t0 = global_ns();
+            if (P.place_mode == 2) {
+                const unsigned sm = sm_id();
+                bool leave = false;
+                if (sm < (unsigned)PlaceBuf::MAX_SM && P.place[PlaceBuf::SKIP + sm])
+                    leave = atomicAdd(P.place + PlaceBuf::CNT + sm, 1) == 0;
+                int it = -1;
+                if (!leave) it = atomicAdd(P.place + PlaceBuf::TICKET, 1);
+                s_item = it < P.place_items ? it : -1;
+            }
+        }
+        if (P.place_mode == 2) {
+            __syncthreads();
+            item = s_item;
+            if (item < 0) {
+                place_epilogue<TY>(P.place, 2, 0, 0ull, reinterpret_cast<int *>(smem_raw), &s_last);
+                return;
+            }
+        }
+    }
     const int H = P.H, Hp = HPC > 0 ? HPC : P.Hp;
 
-    const int yt = blockIdx.x % nyt;
-    // Column range of this CTA: equal chunks, or -- once the engine's balancer has seen a few launches -- the
-    // boundaries it derived from the measured CTA durations (chunk_tab[yt * (nchunks + 1) + c], see rebalance below)
-    const int ck = blockIdx.x / nyt;
-    int xs_ = ck * chunk, xe_ = min(P.Wl, xs_ + chunk);
-    if (P.chunk_tab) {
-        const int *row = P.chunk_tab + (size_t)yt * (gridDim.x / nyt + 1) + ck;
-        xs_ = __ldg(row), xe_ = __ldg(row + 1);
-    }
-    const int xs = xs_, xe = xe_;
+    // strips are the fast index: the CTAs of a column chunk start together and advance in step
+    const int yt = item % nyt;
+    const int ck = item / nyt;
+    const int xs = ck * chunk, xe = min(P.Wl, xs + chunk);
     const int y0 = yt * TY;
     const int y = y0 + t;
     const int ny = min(TY, H - y0);
@@ -487,22 +519,7 @@ __global__ void __launch_bounds__(TY, sizeof(T) == 8 ? FDLBM_FUSED_MINB64 : FDLB
         eq0 = eq1, eq1 = eq2;
     }
     cp_async_wait<0>();
-    if (P.chunk_tab_next) {  // measuring launch (CTA-uniform)
-        __syncthreads();
-        if (t == 0) {
-            P.cta_ticks[blockIdx.x] = (unsigned)s_t0;
-            P.cta_ticks[BAL_CAP_CTA + blockIdx.x] = (unsigned)global_ns();
-            P.cta_ticks[2 * BAL_CAP_CTA + blockIdx.x] = sm_id();
-            __threadfence();
-            s_last = atomicAdd(P.cta_done, 1u) == gridDim.x - 1;
-        }
-        __syncthreads();
-        if (s_last) {
-            __threadfence();
-            rebalance_chunks<T, TY>(P, nyt, chunk, reinterpret_cast<int *>(smem_raw));
-            if (t == 0) *P.cta_done = 0u;
-        }
-    }
+    if (P.place) place_epilogue<TY>(P.place, P.place_mode, P.place_mark, s_t0, reinterpret_cast<int *>(smem_raw), &s_last);
 }
 
 // Column chunk length for `nyt` strips on `n_cta` resident CTA slots.  With c chunks per strip the kernel takes
@@ -527,33 +544,32 @@ inline int fused_chunk(int nyt, int n_cta, int Wl)
     return chunk < 8 ? 8 : chunk;
 }
 
-// host side of the balancer: device buffers owned by the engine + what the next launch should do
-struct ChunkBalancer {
-    static constexpr int CAP_CTA = BAL_CAP_CTA, CAP_TAB = BAL_CAP_TAB;
-    int *tab[2] = {nullptr, nullptr};  // boundary tables, read / written alternately
-    unsigned *ticks = nullptr, *done = nullptr;  // ticks: [3][CAP_CTA] start, end (low 32 bits of ns), %smid
+// host side of the placement: the device block owned by the engine + what the next launch should do
+struct Placement {
+    int *buf = nullptr;        // PlaceBuf::SIZE ints, zero-initialised
     bool enabled = false;
-    int cur = -1;                      // table holding valid boundaries, -1: none yet (equal chunks)
-    int grid = 0, nyt = 0;             // launch shape the boundaries belong to
-    long launches = 0;                 // fused launches of that shape so far
-    int measure_first = 8;             // every one of the first launches measures and rebalances (damping 0.5) ...
-    int measure_every = 64;            // ... then one in so many (damping 0.25); 0: never again
+    bool marked = false;       // the slow SMs of this launch shape are marked: tickets from now on
+    int items = 0, nyt = 0;    // launch shape the marks belong to
+    long launches = 0;         // fused launches of that shape so far
+    int measure_from = 1;      // launches [measure_from, measure_from + measure_n) measure (the first one is cold)
+    int measure_n = 3;
+    int n_skip = 0;            // SMs marked
 };
 
 // returns 0 or a cudaError_t
 template <typename T, int HPC>
-int launch_fused_hp(const LbmParams<T> &P_, cudaStream_t stream, ChunkBalancer *B)
+int launch_fused_hp(const LbmParams<T> &P_, cudaStream_t stream, Placement *B)
 {
     LbmParams<T> P = P_;
     using C = FusedCfg<T, FUSED_TY>;
     auto kern = k_fused<T, FUSED_TY, HPC>;
     // resident CTA slots, cached per device (the shared-memory attribute is a per-device setting too)
-    static int n_cta_of[64] = {0};
+    static int n_cta_of[64] = {0}, n_sm_of[64] = {0};
     int dev = 0;
     if (cudaGetDevice(&dev) != cudaSuccess) return (int)cudaErrorInvalidDevice;
-    int &n_cta = n_cta_of[dev & 63];
+    int &n_cta = n_cta_of[dev & 63], &sms = n_sm_of[dev & 63];
     if (n_cta == 0) {
-        int sms = 0, occ = 0;
+        int occ = 0;
         cudaError_t e;
         e = cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
         if (e != cudaSuccess) return (int)e;
@@ -568,21 +584,30 @@ int launch_fused_hp(const LbmParams<T> &P_, cudaStream_t stream, ChunkBalancer *
     const int nyt = (P.H + FUSED_TY - 1) / FUSED_TY;
     const int chunk = fused_chunk(nyt, n_cta, P.Wl);
     const int nchunks = (P.Wl + chunk - 1) / chunk;
-    const int grid = nyt * nchunks;
-    P.chunk_tab = nullptr;
-    P.chunk_tab_next = nullptr;
-    // measured chunk boundaries: only where the whole grid is ONE resident wave (CTA -> SM placement repeats)
-    if (B && B->enabled && nchunks > 1 && grid <= n_cta && grid <= ChunkBalancer::CAP_CTA && grid + nyt <= ChunkBalancer::CAP_TAB) {
-        if (B->grid != grid || B->nyt != nyt) B->grid = grid, B->nyt = nyt, B->cur = -1, B->launches = 0;
-        if (B->cur >= 0) P.chunk_tab = B->tab[B->cur];
-        const bool first = B->launches < B->measure_first;
-        if (first || (B->measure_every > 0 && B->launches % B->measure_every == 0)) {
-            const int nb = B->cur >= 0 ? 1 - B->cur : 0;
-            P.chunk_tab_next = B->tab[nb];
-            P.cta_ticks = B->ticks;
-            P.cta_done = B->done;
-            P.chunk_alpha = first ? 0.5f : 0.25f;
-            B->cur = nb;  // stream order: the next launch starts after this one has written it
+    const int items = nyt * nchunks;
+    int grid = items;
+    P.place = nullptr;
+    P.place_mode = P.place_items = P.place_mark = 0;
+    // placement: only where the whole grid is ONE resident wave with slots to spare (at most one per SM)
+    const int spare = n_cta - items;
+    if (B && B->enabled && B->buf && spare >= 1 && spare <= sms && sms <= PlaceBuf::MAX_SM && n_cta <= PlaceBuf::CAP_CTA) {
+        if (B->items != items || B->nyt != nyt) {
+            if (B->launches > 0) cudaMemsetAsync(B->buf, 0, PlaceBuf::SIZE * sizeof(int), stream);
+            B->items = items, B->nyt = nyt, B->marked = false, B->launches = 0, B->n_skip = 0;
+        }
+        P.place_items = items;
+        if (B->marked) {
+            P.place = B->buf;
+            P.place_mode = 2;
+            grid = n_cta;
+        } else if (B->launches >= B->measure_from) {
+            P.place = B->buf;
+            P.place_mode = 1;
+            if (B->launches == B->measure_from + B->measure_n - 1) {
+                P.place_mark = spare;
+                B->marked = true;  // stream order: the next launch starts after this one has written the marks
+                B->n_skip = spare;
+            }
         }
         B->launches += 1;
     }
@@ -592,7 +617,7 @@ int launch_fused_hp(const LbmParams<T> &P_, cudaStream_t stream, ChunkBalancer *
 
 // the common row pitches get a kernel with Hp folded into the instruction immediates
 template <typename T>
-int launch_fused(const LbmParams<T> &P, cudaStream_t stream, ChunkBalancer *B = nullptr)
+int launch_fused(const LbmParams<T> &P, cudaStream_t stream, Placement *B = nullptr)
 {
 #ifdef FDLBM_HP_SPECIALISATION  // measured on B200: no gain (19.88 vs 19.93 GLUPS), so off by default
     switch (P.Hp) {

@@ -35,6 +35,9 @@
 #include "lbm_fused_vec.cuh"
 
 namespace fdlbm {
+#ifndef FDLBM_F32_BULK
+#define FDLBM_F32_BULK 0  // 1: g stages filled by cp.async.bulk + mbarrier as in k_fused (A/B knob)
+#endif
 namespace f32p {
 
 typedef float2 p2;
@@ -245,11 +248,47 @@ __global__ void __launch_bounds__(Cfg::NT, 3)
     // strips at the wrap then fill as fast as the others -- the kernel ends with its slowest CTA (+1.8 %)
     const int fyw = fy < 0 ? fy + H : (fy >= H ? fy - H : fy);
     const bool fill_fast = fill_thread && ((H % EPC) == 0 || (fy >= 0 && fy + EPC <= H));
+#if FDLBM_F32_BULK
+    // bulk fill (as in k_fused): one thread issues 9 bulk copies of the contiguous piece of a stage row, completion
+    // counted in bytes on the stage's mbarrier; an apron that wraps in y is one 16-byte cp.async per population
+    __shared__ __align__(8) unsigned long long bars[NS];
+    const bool wrap_lo = y0 - HALO < 0, wrap_hi = y0 + ny + HALO > H;  // CTA-uniform
+    const bool bulk = (!wrap_lo && !wrap_hi) || ((H % EPC) == 0 && (ny % EPC) == 0);
+    if (t == 0) {
+#pragma unroll
+        for (int s_ = 0; s_ < NS; ++s_) mbar_init(&bars[s_], 1);
+        mbar_fence_init();
+    }
+    __syncthreads();
+    auto landed = [&](int c) {
+        if (bulk) mbar_wait(&bars[slot(c)], (unsigned)(((c - (xs - 2)) / NS) & 1));
+    };
+#else
+    constexpr bool bulk = false;
+    auto landed = [](int) {};
+#endif
     auto prefetch = [&](int v) {
         const int cg = v + 2 + D;
         if (cg >= xs - 2 && cg <= xe + 1) {
             T *stage = gst + slot(cg) * FAM + EPC * t;
             const T *col = P.src + lat_idx(Hp, cg, 9, 0);
+#if FDLBM_F32_BULK
+            if (bulk) {
+                T *st0 = gst + slot(cg) * FAM;
+                if (t == 0) {
+                    const int r0 = wrap_lo ? y0 : y0 - HALO;               // first row of the contiguous piece
+                    const int r1 = wrap_hi ? y0 + ny : y0 + ny + HALO;     // one past its last row
+                    const unsigned bytes = (unsigned)((r1 - r0) * sizeof(T));
+                    mbar_expect_tx(&bars[slot(cg)], 9u * bytes);
+#pragma unroll
+                    for (int pop = 0; pop < 9; ++pop)
+                        bulk_g2s(st0 + pop * PT + (r0 - (y0 - HALO)), col + (size_t)pop * Hp + r0, bytes, &bars[slot(cg)]);
+                }
+                if (wrap_lo && t >= 32 && t < 41) cp_async16(st0 + (t - 32) * PT, col + (size_t)(t - 32) * Hp + (y0 - HALO + H));
+                if (wrap_hi && t >= 64 && t < 73)
+                    cp_async16(st0 + (t - 64) * PT + HALO + ny, col + (size_t)(t - 64) * Hp + (y0 + ny - H));
+            } else
+#endif
             if (fill_fast) {
                 const T *s = col + fyw;
 #pragma unroll
@@ -374,12 +413,16 @@ __global__ void __launch_bounds__(Cfg::NT, 3)
             eq1 = load_flags(xs + 2, yef, 1);
         }
         cp_async_wait<D>();
+        landed(xs - 2);
+        landed(xs - 1);
+        landed(xs);
         __syncthreads();
         fl_nxt[0] = decode(rf_m1, yb, 0), fl_nxt[1] = decode(rf_m1, yb, 1);
         psi_column(xs - 1, decode(re_m1, yef, 0) & e_mask, fl_nxt, g_cur, pm, pm_lo, pm_hi);
         __syncthreads();
         prefetch(xs - 1);
         cp_async_wait<D>();
+        landed(xs + 1);
         __syncthreads();
         fl_cur[0] = decode(rf_0, yb, 0), fl_cur[1] = decode(rf_0, yb, 1);
         psi_column(xs, decode(re_0, yef, 0) & e_mask, fl_cur, g_cur, p0, p0_lo, p0_hi);
@@ -398,6 +441,7 @@ __global__ void __launch_bounds__(Cfg::NT, 3)
 
     for (int x = xs; x < xe; ++x) {
         cp_async_wait<D - 1>();  // g column x+2 has landed
+        landed(x + 2);
         __syncthreads();         // ... for every thread; and everybody is done with iteration x-1
         // decode the flags of column x+1 before any new global load is issued (see k_fused)
         unsigned fe_nxt = decode(eq0, yef, 0) & e_mask;

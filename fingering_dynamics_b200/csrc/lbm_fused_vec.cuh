@@ -327,9 +327,9 @@ namespace fdlbm {
 
 // the step kernel used for each storage type
 template <typename T>
-int launch_fused_auto(const LbmParams<T> &P, cudaStream_t stream, ChunkBalancer *B);
+int launch_fused_auto(const LbmParams<T> &P, cudaStream_t stream, Placement *B);
 template <>
-inline int launch_fused_auto<double>(const LbmParams<double> &P, cudaStream_t stream, ChunkBalancer *B)
+inline int launch_fused_auto<double>(const LbmParams<double> &P, cudaStream_t stream, Placement *B)
 {
 #ifdef FDLBM_F64_VEC1
     return launch_fused_vec<double, FUSED_TY, 1>(P, stream);
@@ -338,7 +338,7 @@ inline int launch_fused_auto<double>(const LbmParams<double> &P, cudaStream_t st
 #endif
 }
 template <>
-inline int launch_fused_auto<float>(const LbmParams<float> &P, cudaStream_t stream, ChunkBalancer *B)
+inline int launch_fused_auto<float>(const LbmParams<float> &P, cudaStream_t stream, Placement *B)
 {
 #if FDLBM_F32_VEC == 2
     // even heights: packed two-row kernel (lbm_fused_f32.cuh); FDLBM_F32_KERNEL=vec selects the scalar two-row kernel

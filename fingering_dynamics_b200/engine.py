@@ -183,22 +183,21 @@ class Engine:
         if n:
             raise FloatingPointError("%d non-finite populations after %d iterations" % (n, self.iterations))
 
-    def balance_info(self):
-        """chunk balancer of the fused fp64 step: {'nyt', 'nchunks', 'bounds' (nyt, nchunks+1), 'ticks_ns' (nchunks, nyt),
-        'sm_ids' (nchunks, nyt)}; bounds is None while the chunks are still equal"""
-        nyt, nch = ctypes.c_int32(0), ctypes.c_int32(0)
-        nat.check(nat.lib().fdlbm_balance_info(self._h, ctypes.byref(nyt), ctypes.byref(nch), None, None, None, 0))
-        out = {"nyt": nyt.value, "nchunks": nch.value, "bounds": None, "ticks_ns": None, "sm_ids": None}
-        if nyt.value > 0 and nch.value > 0:
-            b = np.full(nyt.value * (nch.value + 1), -1, dtype=np.int32)
-            t = np.zeros(nyt.value * nch.value, dtype=np.uint32)
-            s = np.zeros(nyt.value * nch.value, dtype=np.uint32)
-            nat.check(nat.lib().fdlbm_balance_info(self._h, ctypes.byref(nyt), ctypes.byref(nch), nat.ptr(b), nat.ptr(t),
-                                                   nat.ptr(s), b.size))
-            if b[0] >= 0:
-                out["bounds"] = b.reshape(nyt.value, nch.value + 1)
-                out["ticks_ns"] = t.reshape(nch.value, nyt.value)
-                out["sm_ids"] = s.reshape(nch.value, nyt.value)
+    def placement_info(self):
+        """CTA placement of the fused fp64 step: {'items', 'marked_sms' (SMs that host one CTA less), 'ticks_ns', 'sm_ids'
+        (per work item, of the last measuring launch)}"""
+        items, nm = ctypes.c_int32(0), ctypes.c_int32(0)
+        nat.check(nat.lib().fdlbm_placement_info(self._h, ctypes.byref(items), ctypes.byref(nm), None, None, None, 0))
+        out = {"items": items.value, "marked_sms": [], "ticks_ns": None, "sm_ids": None}
+        if items.value > 0:
+            cap = max(items.value, 512)
+            m = np.full(cap, -1, dtype=np.int32)
+            t = np.zeros(cap, dtype=np.uint32)
+            s = np.zeros(cap, dtype=np.uint32)
+            nat.check(nat.lib().fdlbm_placement_info(self._h, ctypes.byref(items), ctypes.byref(nm), nat.ptr(m), nat.ptr(t),
+                                                     nat.ptr(s), cap))
+            out["marked_sms"] = m[:nm.value].tolist()
+            out["ticks_ns"], out["sm_ids"] = t[:items.value], s[:items.value]
         return out
 
     def peer_export(self):
