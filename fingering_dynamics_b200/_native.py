@@ -143,8 +143,6 @@ _SIGS = {
     "fdlbm_count_nonfinite": (ctypes.c_int, [ctypes.c_void_p, ctypes.POINTER(ctypes.c_int64)]),
     "fdlbm_peer_export": (ctypes.c_int, [ctypes.c_void_p, ctypes.POINTER(PeerInfo)]),
     "fdlbm_peer_attach": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int, ctypes.POINTER(PeerInfo)]),
-    "fdlbm_placement_info": (ctypes.c_int, [ctypes.c_void_p, ctypes.POINTER(ctypes.c_int32), ctypes.POINTER(ctypes.c_int32),
-                                            ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int]),
     "fdlbm_pinned_alloc": (ctypes.c_void_p, [ctypes.c_size_t]),
     "fdlbm_pinned_free": (None, [ctypes.c_void_p]),
     "fdlbm_op_stream": (ctypes.c_int, [ctypes.c_int, ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p]),

@@ -68,7 +68,6 @@ struct fdlbm_engine {
     int peer_Wl[2] = {0, 0};
     bool peer_ipc[2] = {false, false};
     uint32_t peer_step = 0;                                   // steps taken in peer mode (never reset)
-    Placement placement;                                      // CTA placement of the fused fp64 step (lbm_fused.cuh)
     int cur = 0, pcur = 0;
     int state = ST_EMPTY;
     bool have_geometry = false;
@@ -118,8 +117,6 @@ LbmParams<T> make_params(const fdlbm_engine *e, int src, int psrc)
     P.f3coef = (T)c.outlet_f3_coef;
     P.peer_lo = P.peer_hi = nullptr;
     P.peer_lo_Wl = 0;
-    P.place = nullptr;
-    P.place_mode = P.place_items = P.place_mark = 0;
     return P;
 }
 
@@ -245,7 +242,7 @@ int launch_step(fdlbm_engine *e, bool finalize)
             k_step_twopass<T, false><<<cell_grid(e, e->Wl), TPB, 0, e->stream>>>(P, field_ptrs<T>(e));
         e->launches += 2;
     } else {
-        int rc = launch_fused_auto<T>(P, e->stream, &e->placement);
+        int rc = launch_fused_auto<T>(P, e->stream);
         if (rc) return fail(FDLBM_E_CUDA, "fused launch configuration failed (%d)", rc);
         e->launches += 1;
     }
@@ -555,18 +552,6 @@ int fdlbm_create(const fdlbm_config *cfg, fdlbm_engine **out)
         CUE(cudaMalloc(&e->psi[k], e->plane_elems() * e->esize));
         CUE(cudaMemsetAsync(e->psi[k], 0, e->plane_elems() * e->esize, e->stream));
     }
-    {
-        Placement &B = e->placement;
-        CUE(cudaMalloc((void **)&B.buf, PlaceBuf::SIZE * sizeof(int)));
-        CUE(cudaMemsetAsync(B.buf, 0, PlaceBuf::SIZE * sizeof(int), e->stream));
-        auto env_int = [](const char *name, int dflt) {
-            const char *v = getenv(name);
-            return v && *v ? atoi(v) : dflt;
-        };
-        B.enabled = env_int("FDLBM_PLACEMENT", 1) != 0;
-        B.measure_n = env_int("FDLBM_PLACEMENT_MEASURE", B.measure_n);
-        if (B.measure_n < 1) B.measure_n = 1;
-    }
     CUE(cudaMalloc((void **)&e->flags, 256));
     CUE(cudaMemsetAsync(e->flags, 0, 256, e->stream));
     // the flag arrays carry one spare (zero) column: the step kernels load flags three columns ahead without a bound check
@@ -607,7 +592,7 @@ void fdlbm_destroy(fdlbm_engine *e)
             cudaIpcCloseMemHandle(e->peer_flags[side]);
         }
     void *ptrs[] = {e->lat[0], e->lat[1], e->psi[0], e->psi[1], e->fields, e->reflect, e->solid_bytes,
-                    e->solid, e->inlet, e->outlet, e->staging, e->flags, e->placement.buf};
+                    e->solid, e->inlet, e->outlet, e->staging, e->flags};
     for (void *p : ptrs)
         if (p) cudaFree(p);
     if (e->stream) cudaStreamDestroy(e->stream);
@@ -878,37 +863,6 @@ int fdlbm_peer_attach(fdlbm_engine *e, int side, const fdlbm_peer_info *nb)
         e->peer_ipc[side] = true;
     }
     e->peer_Wl[side] = nb->Wl;
-    return 0;
-}
-
-int fdlbm_placement_info(fdlbm_engine *e, int32_t *items, int32_t *n_marked, int32_t *marked_sms, uint32_t *ticks_ns,
-                         uint32_t *sm_ids, int cap)
-{
-    if (!e || !items || !n_marked) return fail(FDLBM_E_ARG, "null argument");
-    CU(cudaSetDevice(e->cfg.device));
-    CU(cudaStreamSynchronize(e->stream));
-    const Placement &B = e->placement;
-    *items = B.items;
-    *n_marked = B.marked ? B.n_skip : 0;
-    if (!B.buf || B.items <= 0) return 0;
-    if (marked_sms && B.marked) {
-        if (cap < B.n_skip) return fail(FDLBM_E_ARG, "marked_sms needs %d entries", B.n_skip);
-        std::vector<int> skip(PlaceBuf::MAX_SM);
-        CU(cudaMemcpy(skip.data(), B.buf + PlaceBuf::SKIP, skip.size() * sizeof(int), cudaMemcpyDeviceToHost));
-        int n = 0;
-        for (int s = 0; s < PlaceBuf::MAX_SM && n < B.n_skip; ++s)
-            if (skip[s]) marked_sms[n++] = s;
-        *n_marked = n;
-    }
-    if (ticks_ns || sm_ids) {  // of the last measuring launch (grid = items)
-        if (cap < B.items) return fail(FDLBM_E_ARG, "ticks_ns / sm_ids need %d entries", B.items);
-        std::vector<uint32_t> t0(B.items), t1(B.items);
-        CU(cudaMemcpy(t0.data(), B.buf + PlaceBuf::T_BEG, (size_t)B.items * sizeof(int), cudaMemcpyDeviceToHost));
-        CU(cudaMemcpy(t1.data(), B.buf + PlaceBuf::T_END, (size_t)B.items * sizeof(int), cudaMemcpyDeviceToHost));
-        if (ticks_ns)
-            for (int i = 0; i < B.items; ++i) ticks_ns[i] = t1[i] - t0[i];
-        if (sm_ids) CU(cudaMemcpy(sm_ids, B.buf + PlaceBuf::SMID, (size_t)B.items * sizeof(int), cudaMemcpyDeviceToHost));
-    }
     return 0;
 }
 

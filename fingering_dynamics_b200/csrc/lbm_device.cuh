@@ -37,12 +37,6 @@ struct LbmParams {
     // two edge columns straight into their ghost columns (halo exchange fused into the step)
     T *peer_lo, *peer_hi;
     int peer_lo_Wl;           // owned columns of the low-side neighbour (its high ghosts are columns Wl, Wl+1)
-    // CTA placement of the fused fp64 step (lbm_fused.cuh, "placement"): nullptr = CTA i works on item i
-    int *place;               // device block, layout PlaceBuf
-    int place_mode;           // 1: measuring launch (plain mapping, records start / end / %smid per CTA),
-                              // 2: work items are taken by ticket and the SMs marked slow host one CTA less
-    int place_items;          // work items of this launch (strips x column chunks)
-    int place_mark;           // measuring launch: > 0 = mark this many SMs slow once the launch is over
 };
 
 // macroscopic outputs of the finalize pass / inputs of the first collision, each [(xl+G)*Hp + y]

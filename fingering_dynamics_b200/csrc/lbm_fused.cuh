@@ -20,6 +20,8 @@
 // range advance in step and the apron rows a strip reads are L2 hits on lines its neighbour streams.
 // The y wrap is resolved when a stage is filled; the x wrap / slab halo comes from the ghost columns.
 #pragma once
+#include <cstdio>
+#include <cstdlib>
 #include "lbm_device.cuh"
 
 namespace fdlbm {
@@ -40,6 +42,9 @@ namespace fdlbm {
 #endif
 #ifndef FDLBM_BULK_COPY
 #define FDLBM_BULK_COPY 1  // g stages of interior strips through cp.async.bulk + mbarrier (0: per-thread cp.async only)
+#endif
+#ifndef FDLBM_F_STAGED
+#define FDLBM_F_STAGED 1  // the f columns go through a second stage ring (bulk copies); 0: per-thread loads behind an L2 prefetch (measured 2.8 % slower)
 #endif
 constexpr int FUSED_TY = FDLBM_FUSED_TY;  // rows per strip = threads per CTA
 constexpr int FUSED_D = FDLBM_FUSED_D;    // cp.async prefetch distance in columns
@@ -112,7 +117,8 @@ struct FusedCfg {
     static constexpr int PT = TY + 2 * HALO;              // stage row pitch (elements)
     static constexpr int NS = 3 + FUSED_D;                // stages of the g ring (columns x..x+2+D)
     static constexpr int FAM = 9 * PT;                    // elements of one stage (one family of one column)
-    static constexpr size_t SMEM = (size_t)(NS * FAM) * sizeof(T);
+    static constexpr int RINGS = FDLBM_F_STAGED ? 2 : 1;  // g ring (+ f ring)
+    static constexpr size_t SMEM = (size_t)(RINGS * NS * FAM) * sizeof(T);
 };
 
 // Fill one stage: 9 populations of one family of the column whose record starts at `col` (pop 0 of the
@@ -170,102 +176,6 @@ __device__ __forceinline__ void pull_staged(const T *sm, const T *s0, const T *s
     v[8] = *s8;
 }
 
-// ---- placement ---------------------------------------------------------------------------------------------
-// One resident wave ends with its slowest SM, and the spread between SMs is systematic: on B200 a handful of SMs
-// (ids 0, 1, 142-147 on every box measured) need ~5 % longer for the same three CTAs, and the one-wave grid leaves a
-// few CTA slots empty anyway (8192x2048: 432 work items on 444 slots), which the hardware hands to whatever SMs come
-// last in its order.  Two attempts to even this out by moving the column boundaries (per CTA, then per SM) were
-// measured and LOSE 5 % (profiles/README.md): chunks of unequal length pull the strips of a chunk out of lock step,
-// their apron rows stop being L2 hits and the whole machine slows down.  So the chunks stay equal and only the
-// PLACEMENT changes: measuring launches record start / end / %smid of every CTA; the CTA that finishes last adds up
-// the time each SM needed; after the last measuring launch the (slots - items) slowest SMs are marked.  From then
-// on the grid fills every slot, the first CTA to arrive on a marked SM exits at once, and the others take their
-// work item by ticket (strips stay the fast index, so the CTAs of a chunk still start together).  Results do not
-// depend on any of this: every item is worked on by exactly one CTA with the same arithmetic.
-__device__ __forceinline__ unsigned long long global_ns()
-{
-    unsigned long long t;
-    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
-    return t;
-}
-__device__ __forceinline__ unsigned sm_id()
-{
-    unsigned s;
-    asm volatile("mov.u32 %0, %%smid;" : "=r"(s));
-    return s;
-}
-struct PlaceBuf {  // offsets (ints) into LbmParams::place
-    static constexpr int MAX_SM = 512, CAP_CTA = 2048;
-    static constexpr int TICKET = 0, DONE = 1, MEASURED = 2;
-    static constexpr int SKIP = 16, CNT = SKIP + MAX_SM, ACC = CNT + MAX_SM;
-    static constexpr int T_BEG = ACC + MAX_SM, T_END = T_BEG + CAP_CTA, SMID = T_END + CAP_CTA, SIZE = SMID + CAP_CTA;
-};
-
-// measuring launch, CTA that finished last: time per SM of this launch added to ACC; optionally mark the slowest.
-// `scratch`: >= 3 * MAX_SM ints of shared memory (the g stages, no longer in use)
-template <int TY>
-__device__ __noinline__ void place_account(int *pb, int grid, int mark, int *scratch)
-{
-    constexpr int MAX_SM = PlaceBuf::MAX_SM;
-    int *sm_n = scratch, *sm_t0 = scratch + MAX_SM, *sm_t1 = scratch + 2 * MAX_SM;
-    const unsigned *t_beg = (const unsigned *)pb + PlaceBuf::T_BEG, *t_end = (const unsigned *)pb + PlaceBuf::T_END;
-    const unsigned *smid = (const unsigned *)pb + PlaceBuf::SMID;
-    for (int s = threadIdx.x; s < MAX_SM; s += TY) sm_n[s] = 0, sm_t0[s] = 0x7fffffff, sm_t1[s] = -0x7fffffff;
-    __syncthreads();
-    const unsigned ref = __ldcg(t_beg);  // times relative to the start of CTA 0 (32-bit ns differences)
-    for (int i = threadIdx.x; i < grid; i += TY) {
-        const unsigned s = __ldcg(smid + i);
-        if (s < (unsigned)MAX_SM) {
-            atomicAdd(&sm_n[s], 1);
-            atomicMin(&sm_t0[s], (int)(__ldcg(t_beg + i) - ref));
-            atomicMax(&sm_t1[s], (int)(__ldcg(t_end + i) - ref));
-        }
-    }
-    __syncthreads();
-    int nmax = 0;
-    for (int s = 0; s < MAX_SM; ++s) nmax = max(nmax, sm_n[s]);
-    for (int s = threadIdx.x; s < MAX_SM; s += TY) {
-        // only SMs that carried the full number of CTAs are comparable; the others count as fast
-        const int dt = sm_n[s] == nmax ? sm_t1[s] - sm_t0[s] : 0;
-        pb[PlaceBuf::ACC + s] += dt;
-        sm_t0[s] = pb[PlaceBuf::ACC + s];
-    }
-    __syncthreads();
-    if (mark > 0)
-        for (int s = threadIdx.x; s < MAX_SM; s += TY) {
-            const int mine = sm_t0[s];
-            int rank = 0;
-            for (int o = 0; o < MAX_SM; ++o) rank += (sm_t0[o] > mine) || (sm_t0[o] == mine && o < s);
-            pb[PlaceBuf::SKIP + s] = (mine > 0 && rank < mark) ? 1 : 0;
-        }
-}
-
-// end of every CTA of a launch with placement (also of the CTAs that exit without work)
-template <int TY>
-__device__ __forceinline__ void place_epilogue(int *pb, int mode, int mark, unsigned long long t0, int *scratch, int *s_last)
-{
-    __syncthreads();
-    if (threadIdx.x == 0) {
-        if (mode == 1) {
-            pb[PlaceBuf::T_BEG + blockIdx.x] = (int)(unsigned)t0;
-            pb[PlaceBuf::T_END + blockIdx.x] = (int)(unsigned)global_ns();
-            pb[PlaceBuf::SMID + blockIdx.x] = (int)sm_id();
-        }
-        __threadfence();
-        *s_last = atomicAdd(pb + PlaceBuf::DONE, 1) == (int)gridDim.x - 1;
-    }
-    __syncthreads();
-    if (*s_last) {  // everybody else is done: account / reset for the next launch
-        __threadfence();
-        if (mode == 1) {
-            place_account<TY>(pb, (int)gridDim.x, mark, scratch);
-        } else {
-            for (int s = threadIdx.x; s < PlaceBuf::MAX_SM; s += TY) pb[PlaceBuf::CNT + s] = 0;
-        }
-        if (threadIdx.x == 0) pb[PlaceBuf::TICKET] = 0, pb[PlaceBuf::DONE] = 0, pb[PlaceBuf::MEASURED] += mode == 1;
-    }
-}
-
 struct RawFlags {
     unsigned refl, word;  // reflect byte and solid-mask word exactly as loaded
 };
@@ -280,39 +190,18 @@ __global__ void __launch_bounds__(TY, sizeof(T) == 8 ? FDLBM_FUSED_MINB64 : FDLB
     constexpr unsigned FULL = 0xffffffffu;
     extern __shared__ __align__(16) unsigned char smem_raw[];
     T *gst = reinterpret_cast<T *>(smem_raw);        // [NS][9][PT]
+    T *fst = gst + NS * FAM;                         // [NS][9][PT], FDLBM_F_STAGED only
     __shared__ __align__(8) unsigned long long bars[NS];  // one mbarrier per g stage (bulk-copy path)
-    __shared__ unsigned long long s_t0;                   // placement: start time of this CTA (measuring launch)
-    __shared__ int s_last, s_item;
     const int t = threadIdx.x, lane = t & 31;
-    // work item of this CTA: its block index, or -- once the engine has marked the slow SMs -- a ticket
-    int item = blockIdx.x;
-    if (P.place) {  // CTA-uniform
-        if (t == 0) {
-            if (P.place_mode == 1) s_t0 = global_ns();
-            if (P.place_mode == 2) {
-                const unsigned sm = sm_id();
-                bool leave = false;
-                if (sm < (unsigned)PlaceBuf::MAX_SM && P.place[PlaceBuf::SKIP + sm])
-                    leave = atomicAdd(P.place + PlaceBuf::CNT + sm, 1) == 0;
-                int it = -1;
-                if (!leave) it = atomicAdd(P.place + PlaceBuf::TICKET, 1);
-                s_item = it < P.place_items ? it : -1;
-            }
-        }
-        if (P.place_mode == 2) {
-            __syncthreads();
-            item = s_item;
-            if (item < 0) {
-                place_epilogue<TY>(P.place, 2, 0, 0ull, reinterpret_cast<int *>(smem_raw), &s_last);
-                return;
-            }
-        }
-    }
     const int H = P.H, Hp = HPC > 0 ? HPC : P.Hp;
 
-    // strips are the fast index: the CTAs of a column chunk start together and advance in step
-    const int yt = item % nyt;
-    const int ck = item / nyt;
+    // strips are the fast CTA index: the CTAs of a column chunk start together and advance in step.  The chunks
+    // are EQUAL and the hardware places the CTAs: evening out the CTA / SM finishing times (the launch ends with
+    // its slowest SM, ~5 % after the median one) by measured chunk lengths or by placement was tried three ways in
+    // round 2 and lost 2-5 % every time (profiles/README.md, profiles/r2/tail_experiments/): anything that pulls the
+    // strips of a chunk out of lock step costs more in L2 / DRAM locality than the tail it removes.
+    const int yt = blockIdx.x % nyt;
+    const int ck = blockIdx.x / nyt;
     const int xs = ck * chunk, xe = min(P.Wl, xs + chunk);
     const int y0 = yt * TY;
     const int y = y0 + t;
@@ -352,22 +241,32 @@ __global__ void __launch_bounds__(TY, sizeof(T) == 8 ? FDLBM_FUSED_MINB64 : FDLB
     }
     __syncthreads();
 
-    // one pipeline step: g column v+2+D; only columns this run reads
+    // one pipeline step: g column v+2+D (and, FDLBM_F_STAGED, f column v+1+D: f is consumed one column behind g, so
+    // its ring holds x-1..x+1 plus the column in flight); only columns this run reads.  Whenever an f column is
+    // fetched a g column is fetched with it, on the same mbarrier / commit group.
     auto prefetch = [&](int v) {
         const int cg = v + 2 + D;
         if (cg >= xs - 2 && cg <= xe + 1) {
             T *stage = gst + slot(cg) * FAM;
             const T *col = P.src + lat_idx(Hp, cg, 9, 0);
+            const bool with_f = FDLBM_F_STAGED && cg - 1 >= xs - 1 && cg - 1 <= xe;
+            T *fstage = fst + slot(cg - 1) * FAM;
+            const T *fcol = P.src + lat_idx(Hp, cg - 1, 0, 0);
             if (bulk) {
                 // one bulk copy per population for the contiguous piece of the stage row ...
                 if (t == 0) {
                     const int r0 = wrap_lo ? y0 : y0 - HALO;               // its first row
                     const int r1 = wrap_hi ? y0 + ny : y0 + ny + HALO;     // one past its last row
                     const unsigned bytes = (unsigned)((r1 - r0) * sizeof(T));
-                    mbar_expect_tx(&bars[slot(cg)], 9u * bytes);
+                    mbar_expect_tx(&bars[slot(cg)], (with_f ? 18u : 9u) * bytes);
 #pragma unroll
                     for (int pop = 0; pop < 9; ++pop)
                         bulk_g2s(stage + pop * PT + (r0 - (y0 - HALO)), col + (size_t)pop * Hp + r0, bytes, &bars[slot(cg)]);
+                    if (with_f) {
+#pragma unroll
+                        for (int pop = 0; pop < 9; ++pop)
+                            bulk_g2s(fstage + pop * PT + (r0 - (y0 - HALO)), fcol + (size_t)pop * Hp + r0, bytes, &bars[slot(cg)]);
+                    }
                 }
                 // ... and one 16-byte cp.async per population for an apron that wraps in y (16-byte bulk copies
                 // measured far slower: 17.0 instead of 19.5 GLUPS)
@@ -375,8 +274,15 @@ __global__ void __launch_bounds__(TY, sizeof(T) == 8 ? FDLBM_FUSED_MINB64 : FDLB
                     cp_async16(stage + (t - 32) * PT, col + (size_t)(t - 32) * Hp + (y0 - HALO + H));
                 if (wrap_hi && t >= 64 && t < 73)
                     cp_async16(stage + (t - 64) * PT + HALO + ny, col + (size_t)(t - 64) * Hp + (y0 + ny - H));
+                if (with_f) {
+                    if (wrap_lo && t >= 41 && t < 50)
+                        cp_async16(fstage + (t - 41) * PT, fcol + (size_t)(t - 41) * Hp + (y0 - HALO + H));
+                    if (wrap_hi && t >= 73 && t < 82)
+                        cp_async16(fstage + (t - 73) * PT + HALO + ny, fcol + (size_t)(t - 73) * Hp + (y0 + ny - H));
+                }
             } else {
                 stage_fill<T, TY, PT, HALO>(stage, col, Hp, H, y0, ny);
+                if (with_f) stage_fill<T, TY, PT, HALO>(fstage, fcol, Hp, H, y0, ny);
             }
         }
         cp_async_commit();
@@ -474,12 +380,19 @@ __global__ void __launch_bounds__(TY, sizeof(T) == 8 ? FDLBM_FUSED_MINB64 : FDLB
         T f[9];
         {
             // f of column x straight into registers; consumed after the psi phase below
+#if FDLBM_F_STAGED
+            if (active)
+                pull_staged<T, PT>(fst + slot(x - 1) * FAM, fst + slot(x) * FAM, fst + slot(x + 1) * FAM, j, fl_cur & 0xffu, f);
+#else
             if (active) pull_hp(P, Hp, x, y, 0, fl_cur & 0xffu, f);
+#endif
             // and the lines of f column x+L2_AHEAD into L2: one prefetch per 128-byte line of the strip
             constexpr int LPP = (TY * (int)sizeof(T) + 127) / 128;  // lines per population row
             const int cf = x + FUSED_L2_AHEAD;
             const int tt = TY - 1 - t;  // the cp.async issue above kept the low warps busy: use the high ones
-            if (FDLBM_L2_BULK) {
+            if (FDLBM_F_STAGED) {
+                // no L2 prefetch: the bulk copy of an f column is itself issued two columns ahead of its use
+            } else if (FDLBM_L2_BULK) {
                 if (FUSED_L2_AHEAD > 0 && tt < 9 && cf <= xe + 1)
                     prefetch_l2_bulk(P.src + lat_idx(Hp, cf, tt, y0), (unsigned)((ny * (int)sizeof(T) + 15) & ~15));
             } else if (FUSED_L2_AHEAD > 0 && tt < 9 * LPP && cf <= xe + 1) {
@@ -519,7 +432,6 @@ __global__ void __launch_bounds__(TY, sizeof(T) == 8 ? FDLBM_FUSED_MINB64 : FDLB
         eq0 = eq1, eq1 = eq2;
     }
     cp_async_wait<0>();
-    if (P.place) place_epilogue<TY>(P.place, P.place_mode, P.place_mark, s_t0, reinterpret_cast<int *>(smem_raw), &s_last);
 }
 
 // Column chunk length for `nyt` strips on `n_cta` resident CTA slots.  With c chunks per strip the kernel takes
@@ -544,32 +456,19 @@ inline int fused_chunk(int nyt, int n_cta, int Wl)
     return chunk < 8 ? 8 : chunk;
 }
 
-// host side of the placement: the device block owned by the engine + what the next launch should do
-struct Placement {
-    int *buf = nullptr;        // PlaceBuf::SIZE ints, zero-initialised
-    bool enabled = false;
-    bool marked = false;       // the slow SMs of this launch shape are marked: tickets from now on
-    int items = 0, nyt = 0;    // launch shape the marks belong to
-    long launches = 0;         // fused launches of that shape so far
-    int measure_from = 1;      // launches [measure_from, measure_from + measure_n) measure (the first one is cold)
-    int measure_n = 3;
-    int n_skip = 0;            // SMs marked
-};
-
 // returns 0 or a cudaError_t
 template <typename T, int HPC>
-int launch_fused_hp(const LbmParams<T> &P_, cudaStream_t stream, Placement *B)
+int launch_fused_hp(const LbmParams<T> &P, cudaStream_t stream)
 {
-    LbmParams<T> P = P_;
     using C = FusedCfg<T, FUSED_TY>;
     auto kern = k_fused<T, FUSED_TY, HPC>;
     // resident CTA slots, cached per device (the shared-memory attribute is a per-device setting too)
-    static int n_cta_of[64] = {0}, n_sm_of[64] = {0};
+    static int n_cta_of[64] = {0};
     int dev = 0;
     if (cudaGetDevice(&dev) != cudaSuccess) return (int)cudaErrorInvalidDevice;
-    int &n_cta = n_cta_of[dev & 63], &sms = n_sm_of[dev & 63];
+    int &n_cta = n_cta_of[dev & 63];
     if (n_cta == 0) {
-        int occ = 0;
+        int sms = 0, occ = 0;
         cudaError_t e;
         e = cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
         if (e != cudaSuccess) return (int)e;
@@ -579,55 +478,29 @@ int launch_fused_hp(const LbmParams<T> &P_, cudaStream_t stream, Placement *B)
         if (e != cudaSuccess) return (int)e;
         if (occ < 1) occ = 1;
         n_cta = sms * occ;
+        if (getenv("FDLBM_DEBUG")) fprintf(stderr, "fdlbm: k_fused %d B smem, %d CTAs/SM x %d SMs\n", (int)C::SMEM, occ, sms);
     }
     // column chunks per strip, all strips of a chunk in step (strips are the fast CTA index)
     const int nyt = (P.H + FUSED_TY - 1) / FUSED_TY;
     const int chunk = fused_chunk(nyt, n_cta, P.Wl);
     const int nchunks = (P.Wl + chunk - 1) / chunk;
-    const int items = nyt * nchunks;
-    int grid = items;
-    P.place = nullptr;
-    P.place_mode = P.place_items = P.place_mark = 0;
-    // placement: only where the whole grid is ONE resident wave with slots to spare (at most one per SM)
-    const int spare = n_cta - items;
-    if (B && B->enabled && B->buf && spare >= 1 && spare <= sms && sms <= PlaceBuf::MAX_SM && n_cta <= PlaceBuf::CAP_CTA) {
-        if (B->items != items || B->nyt != nyt) {
-            if (B->launches > 0) cudaMemsetAsync(B->buf, 0, PlaceBuf::SIZE * sizeof(int), stream);
-            B->items = items, B->nyt = nyt, B->marked = false, B->launches = 0, B->n_skip = 0;
-        }
-        P.place_items = items;
-        if (B->marked) {
-            P.place = B->buf;
-            P.place_mode = 2;
-            grid = n_cta;
-        } else if (B->launches >= B->measure_from) {
-            P.place = B->buf;
-            P.place_mode = 1;
-            if (B->launches == B->measure_from + B->measure_n - 1) {
-                P.place_mark = spare;
-                B->marked = true;  // stream order: the next launch starts after this one has written the marks
-                B->n_skip = spare;
-            }
-        }
-        B->launches += 1;
-    }
-    kern<<<grid, FUSED_TY, C::SMEM, stream>>>(P, nyt, chunk);
+    kern<<<nyt * nchunks, FUSED_TY, C::SMEM, stream>>>(P, nyt, chunk);
     return 0;
 }
 
 // the common row pitches get a kernel with Hp folded into the instruction immediates
 template <typename T>
-int launch_fused(const LbmParams<T> &P, cudaStream_t stream, Placement *B = nullptr)
+int launch_fused(const LbmParams<T> &P, cudaStream_t stream)
 {
 #ifdef FDLBM_HP_SPECIALISATION  // measured on B200: no gain (19.88 vs 19.93 GLUPS), so off by default
     switch (P.Hp) {
-    case 2048: return launch_fused_hp<T, 2048>(P, stream, B);
-    case 4096: return launch_fused_hp<T, 4096>(P, stream, B);
-    case 8192: return launch_fused_hp<T, 8192>(P, stream, B);
+    case 2048: return launch_fused_hp<T, 2048>(P, stream);
+    case 4096: return launch_fused_hp<T, 4096>(P, stream);
+    case 8192: return launch_fused_hp<T, 8192>(P, stream);
     default: break;
     }
 #endif
-    return launch_fused_hp<T, 0>(P, stream, B);
+    return launch_fused_hp<T, 0>(P, stream);
 }
 
 }  // namespace fdlbm

@@ -36,7 +36,10 @@
 
 namespace fdlbm {
 #ifndef FDLBM_F32_BULK
-#define FDLBM_F32_BULK 0  // 1: g stages filled by cp.async.bulk + mbarrier as in k_fused (A/B knob)
+#define FDLBM_F32_BULK 1  // g stages filled by cp.async.bulk + mbarrier as in k_fused (measured +2.8 % over per-thread cp.async; 0 for A/B)
+#endif
+#ifndef FDLBM_F32_FSTAGED
+#define FDLBM_F32_FSTAGED 1  // the f columns go through a second stage ring (measured +1.5 %); 0: per-thread global loads behind an L2 prefetch
 #endif
 namespace f32p {
 
@@ -92,7 +95,8 @@ FDLBM_DI float lds_f(const float *p)
 
 struct Cfg {
     static constexpr int NT = 128, ROWS = 256, HALO = 4, PT = ROWS + 2 * HALO, NS = 4, FAM = 9 * PT;
-    static constexpr size_t SMEM = (size_t)NS * FAM * sizeof(float);
+    static constexpr int RINGS = FDLBM_F32_FSTAGED ? 2 : 1;  // g ring (+ f ring)
+    static constexpr size_t SMEM = (size_t)RINGS * NS * FAM * sizeof(float);
 };
 
 // moments of the cell pair (fingering_periodic.py:123-152, 201-208), packed; see moments() in lbm_device.cuh
@@ -201,7 +205,7 @@ __global__ void __launch_bounds__(Cfg::NT, 3)
     constexpr int D = FUSED_D, NS = Cfg::NS, PT = Cfg::PT, HALO = Cfg::HALO, FAM = Cfg::FAM, ROWS = Cfg::ROWS, NT = Cfg::NT;
     constexpr unsigned FULL = 0xffffffffu;
     static_assert(D == 1 && NS == 4, "stage ring of four columns, one column ahead");
-    static_assert(VecCfg<float, NT, 2>::SMEM == Cfg::SMEM && VecCfg<float, NT, 2>::ROWS == ROWS, "same strips as k_fused_vec");
+    static_assert(VecCfg<float, NT, 2>::SMEM <= Cfg::SMEM && VecCfg<float, NT, 2>::ROWS == ROWS, "same strips as k_fused_vec");
     if ((int)blockIdx.x >= n_fast) {  // face CTA
         const int k = (int)blockIdx.x - n_fast, side = k / nyt;
         const bool left = fx0 > 0 && side == 0;
@@ -210,6 +214,7 @@ __global__ void __launch_bounds__(Cfg::NT, 3)
     }
     extern __shared__ __align__(16) unsigned char smem_raw[];
     T *gst = reinterpret_cast<T *>(smem_raw);  // [NS][9][PT]
+    T *fst = gst + NS * FAM;                   // [NS][9][PT], FDLBM_F32_FSTAGED only
     const int t = threadIdx.x, lane = t & 31;
     const int H = P.H, Hp = HPC > 0 ? HPC : P.Hp;
     const ptrdiff_t S = (ptrdiff_t)NPOP * Hp;  // column stride (elements)
@@ -267,40 +272,61 @@ __global__ void __launch_bounds__(Cfg::NT, 3)
     constexpr bool bulk = false;
     auto landed = [](int) {};
 #endif
+    // g column v+2+D and (FDLBM_F32_FSTAGED) f column v+1+D: f is consumed one column behind g, its ring holds
+    // x-1..x+1 plus the column in flight; an f column always travels with a g column (same mbarrier / commit group)
     auto prefetch = [&](int v) {
         const int cg = v + 2 + D;
         if (cg >= xs - 2 && cg <= xe + 1) {
             T *stage = gst + slot(cg) * FAM + EPC * t;
             const T *col = P.src + lat_idx(Hp, cg, 9, 0);
+            const bool with_f = FDLBM_F32_FSTAGED && cg - 1 >= xs - 1 && cg - 1 <= xe;
+            T *fstage = fst + slot(cg - 1) * FAM + EPC * t;
+            const T *fcol = P.src + lat_idx(Hp, cg - 1, 0, 0);
 #if FDLBM_F32_BULK
             if (bulk) {
-                T *st0 = gst + slot(cg) * FAM;
+                T *st0 = gst + slot(cg) * FAM, *fs0 = fst + slot(cg - 1) * FAM;
                 if (t == 0) {
                     const int r0 = wrap_lo ? y0 : y0 - HALO;               // first row of the contiguous piece
                     const int r1 = wrap_hi ? y0 + ny : y0 + ny + HALO;     // one past its last row
                     const unsigned bytes = (unsigned)((r1 - r0) * sizeof(T));
-                    mbar_expect_tx(&bars[slot(cg)], 9u * bytes);
+                    mbar_expect_tx(&bars[slot(cg)], (with_f ? 18u : 9u) * bytes);
 #pragma unroll
                     for (int pop = 0; pop < 9; ++pop)
                         bulk_g2s(st0 + pop * PT + (r0 - (y0 - HALO)), col + (size_t)pop * Hp + r0, bytes, &bars[slot(cg)]);
+                    if (with_f) {
+#pragma unroll
+                        for (int pop = 0; pop < 9; ++pop)
+                            bulk_g2s(fs0 + pop * PT + (r0 - (y0 - HALO)), fcol + (size_t)pop * Hp + r0, bytes, &bars[slot(cg)]);
+                    }
                 }
                 if (wrap_lo && t >= 32 && t < 41) cp_async16(st0 + (t - 32) * PT, col + (size_t)(t - 32) * Hp + (y0 - HALO + H));
                 if (wrap_hi && t >= 64 && t < 73)
                     cp_async16(st0 + (t - 64) * PT + HALO + ny, col + (size_t)(t - 64) * Hp + (y0 + ny - H));
+                if (with_f) {
+                    if (wrap_lo && t >= 41 && t < 50) cp_async16(fs0 + (t - 41) * PT, fcol + (size_t)(t - 41) * Hp + (y0 - HALO + H));
+                    if (wrap_hi && t >= 73 && t < 82)
+                        cp_async16(fs0 + (t - 73) * PT + HALO + ny, fcol + (size_t)(t - 73) * Hp + (y0 + ny - H));
+                }
             } else
 #endif
             if (fill_fast) {
-                const T *s = col + fyw;
+                const T *s = col + fyw, *sf = fcol + fyw;
 #pragma unroll
                 for (int pop = 0; pop < 9; ++pop) cp_async16(stage + pop * PT, s + (ptrdiff_t)pop * Hp);
+                if (with_f) {
+#pragma unroll
+                    for (int pop = 0; pop < 9; ++pop) cp_async16(fstage + pop * PT, sf + (ptrdiff_t)pop * Hp);
+                }
             } else if (fill_thread) {
 #pragma unroll
                 for (int e = 0; e < EPC; ++e) {
                     int yy = (fy + e) % H;
                     if (yy < 0) yy += H;
 #pragma unroll
-                    for (int pop = 0; pop < 9; ++pop)
+                    for (int pop = 0; pop < 9; ++pop) {
                         cp_async_small<4>(stage + pop * PT + e, col + (size_t)pop * Hp + yy);
+                        if (with_f) cp_async_small<4>(fstage + pop * PT + e, fcol + (size_t)pop * Hp + yy);
+                    }
                 }
             }
         }
@@ -321,8 +347,8 @@ __global__ void __launch_bounds__(Cfg::NT, 3)
     };
 
     // g of the row pair of column c after streaming + bounce-back, straight from the stages
-    auto pull_pair_g = [&](int c, unsigned b0bits, unsigned b1bits, bool anyb, p2 g[9]) {
-        const T *qm = gst + slot(c - 1) * FAM + jb, *q0 = gst + slot(c) * FAM + jb, *qp = gst + slot(c + 1) * FAM + jb;
+    auto pull_pair = [&](const T *ring, int c, unsigned b0bits, unsigned b1bits, bool anyb, p2 g[9]) {
+        const T *qm = ring + slot(c - 1) * FAM + jb, *q0 = ring + slot(c) * FAM + jb, *qp = ring + slot(c + 1) * FAM + jb;
         if (!anyb) {
             g[1] = *reinterpret_cast<const p2 *>(qm + 1 * PT);
             g[3] = *reinterpret_cast<const p2 *>(qp + 3 * PT);
@@ -345,6 +371,7 @@ __global__ void __launch_bounds__(Cfg::NT, 3)
         }
         g[0] = lds_v2(q0);  // last: a predicated load is never the tail of its block (see ldg_v2)
     };
+    auto pull_pair_g = [&](int c, unsigned b0bits, unsigned b1bits, bool anyb, p2 g[9]) { pull_pair(gst, c, b0bits, b1bits, anyb, g); };
     // psi_new of column c on the row pair (q) and on its outer neighbours (q_lo, q_hi); every column a fast CTA
     // touches is in the domain and carries no Zou-He rule.  KEEP = false: the pulled g is dropped -- the collision
     // of column c reloads it from the stages one iteration later (pull_pair_g), which is cheaper than 18
@@ -451,6 +478,9 @@ __global__ void __launch_bounds__(Cfg::NT, 3)
         {   // f of column x: stream + bounce-back straight into registers
             const unsigned b0bits = fl_cur[0] & 0xffu, b1bits = fl_cur[1] & 0xffu;
             const bool anyb = __any_sync(FULL, has && ((b0bits | b1bits) != 0u));
+#if FDLBM_F32_FSTAGED
+            if (has) pull_pair(fst, x, b0bits, b1bits, anyb, f);
+#else
             if (has) {
                 const T *pmn = pc + dm, *ppl = pc + dp;  // rows yb-1 / yb+2 (wrapped)
                 if (!anyb) {
@@ -475,13 +505,16 @@ __global__ void __launch_bounds__(Cfg::NT, 3)
                 }
                 f[0] = ldg_v2(pc);
             }
+#endif
         }
         prefetch(x);  // after the f loads: f is what the iteration waits for first (+0.9 %)
         {   // the lines of f column x+L2_AHEAD into L2: one prefetch per 128-byte line of the strip
             constexpr int LPP = (ROWS * (int)sizeof(T) + 127) / 128;
             const int cf = x + FUSED_L2_AHEAD;
             const int tt = NT - 1 - t;  // the cp.async issue above kept the low warps busy: use the high ones
-            if (FDLBM_L2_BULK) {
+            if (FDLBM_F32_FSTAGED) {
+                // no L2 prefetch: the stage fill of an f column is itself issued two columns ahead of its use
+            } else if (FDLBM_L2_BULK) {
                 if (FUSED_L2_AHEAD > 0 && tt < 9 && cf <= xe + 1)
                     prefetch_l2_bulk(P.src + lat_idx(Hp, cf, tt, y0),
                                      (unsigned)((min(ROWS, H - y0) * (int)sizeof(T) + 15) & ~15));

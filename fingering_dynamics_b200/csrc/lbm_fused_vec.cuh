@@ -327,18 +327,18 @@ namespace fdlbm {
 
 // the step kernel used for each storage type
 template <typename T>
-int launch_fused_auto(const LbmParams<T> &P, cudaStream_t stream, Placement *B);
+int launch_fused_auto(const LbmParams<T> &P, cudaStream_t stream);
 template <>
-inline int launch_fused_auto<double>(const LbmParams<double> &P, cudaStream_t stream, Placement *B)
+inline int launch_fused_auto<double>(const LbmParams<double> &P, cudaStream_t stream)
 {
 #ifdef FDLBM_F64_VEC1
     return launch_fused_vec<double, FUSED_TY, 1>(P, stream);
 #else
-    return launch_fused<double>(P, stream, B);
+    return launch_fused<double>(P, stream);
 #endif
 }
 template <>
-inline int launch_fused_auto<float>(const LbmParams<float> &P, cudaStream_t stream, Placement *B)
+inline int launch_fused_auto<float>(const LbmParams<float> &P, cudaStream_t stream)
 {
 #if FDLBM_F32_VEC == 2
     // even heights: packed two-row kernel (lbm_fused_f32.cuh); FDLBM_F32_KERNEL=vec selects the scalar two-row kernel

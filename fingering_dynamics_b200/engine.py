@@ -183,23 +183,6 @@ class Engine:
         if n:
             raise FloatingPointError("%d non-finite populations after %d iterations" % (n, self.iterations))
 
-    def placement_info(self):
-        """CTA placement of the fused fp64 step: {'items', 'marked_sms' (SMs that host one CTA less), 'ticks_ns', 'sm_ids'
-        (per work item, of the last measuring launch)}"""
-        items, nm = ctypes.c_int32(0), ctypes.c_int32(0)
-        nat.check(nat.lib().fdlbm_placement_info(self._h, ctypes.byref(items), ctypes.byref(nm), None, None, None, 0))
-        out = {"items": items.value, "marked_sms": [], "ticks_ns": None, "sm_ids": None}
-        if items.value > 0:
-            cap = max(items.value, 512)
-            m = np.full(cap, -1, dtype=np.int32)
-            t = np.zeros(cap, dtype=np.uint32)
-            s = np.zeros(cap, dtype=np.uint32)
-            nat.check(nat.lib().fdlbm_placement_info(self._h, ctypes.byref(items), ctypes.byref(nm), nat.ptr(m), nat.ptr(t),
-                                                     nat.ptr(s), cap))
-            out["marked_sms"] = m[:nm.value].tolist()
-            out["ticks_ns"], out["sm_ids"] = t[:items.value], s[:items.value]
-        return out
-
     def peer_export(self):
         """bytes describing this engine's lattices and flag words (fdlbm_peer_info) for a neighbouring engine"""
         info = nat.PeerInfo()

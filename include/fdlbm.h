@@ -178,15 +178,6 @@ typedef struct {
 int fdlbm_peer_export(fdlbm_engine *e, fdlbm_peer_info *out);
 int fdlbm_peer_attach(fdlbm_engine *e, int side, const fdlbm_peer_info *nb);
 
-/* Diagnostics of the fused fp64 step's CTA placement (csrc/lbm_fused.cuh; no counterpart in the reference): the
- * step kernel runs as one resident wave of (strips x column chunks) work items; its first launches record when and on
- * which SM every CTA ran, after which the SMs that needed longest host one CTA less (the one-wave grid has a few
- * spare CTA slots).  Returns the work items per launch, the SMs marked slow (`marked_sms`, up to `cap`), and of the
- * last measuring launch the CTA durations in ns and the SM of each CTA ([item], `cap` >= items).
- * FDLBM_PLACEMENT=0 in the environment switches the placement off.  Results never depend on it. */
-int fdlbm_placement_info(fdlbm_engine *e, int32_t *items, int32_t *n_marked, int32_t *marked_sms, uint32_t *ticks_ns,
-                         uint32_t *sm_ids, int cap);
-
 /* page-locked host memory for the e2e path */
 void *fdlbm_pinned_alloc(size_t bytes);
 void fdlbm_pinned_free(void *p);
