@@ -228,7 +228,6 @@ __global__ void __launch_bounds__(TY, sizeof(T) == 8 ? FDLBM_FUSED_MINB64 : FDLB
     // Interior strips (no y wrap inside the apron) fill their g stages with BULK asynchronous copies: one thread
     // issues 9 cp.async.bulk of a whole stage row each (1056 bytes), completion is counted in bytes on the stage's
     // mbarrier.  Strips that touch the wrap use per-thread 16-byte cp.async (stage_fill).
-    constexpr unsigned ROW_BYTES = (unsigned)(PT * sizeof(T));
     // Strips whose apron wraps in y copy the contiguous piece in bulk and the wrapped apron with 16-byte cp.async when
     // the pieces keep the 16-byte granularity; the kernel ends with its slowest CTA, and strips on the per-thread path
     // were that CTA.

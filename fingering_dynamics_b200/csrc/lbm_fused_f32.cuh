@@ -456,9 +456,11 @@ __global__ void __launch_bounds__(Cfg::NT, 3)
     }
 
     // ---- running pointers: everything the iteration touches is pointer + immediate -----------------------
+#if !FDLBM_F32_FSTAGED
     const int dm = (yb - 1 < 0 ? yb - 1 + H : yb - 1) - yb;      // f streams with the periodic wrap (np.roll) ...
     const int dp = (yb + 2 >= H ? yb + 2 - H : yb + 2) - yb;     // ... whatever the psi ghost rows are
     const T *pc = P.src + lat_idx(Hp, xs, 0, 0) + yb;            // column x, row yb
+#endif
     T *pd = P.dst + lat_idx(Hp, xs, 0, 0) + yb;
     // flags of column x+3: own pair / this lane's outer row
     const uint8_t *fr_own = P.reflect + cell_idx(Hp, xs + 3, 0) + yb;
@@ -582,7 +584,10 @@ __global__ void __launch_bounds__(Cfg::NT, 3)
         fl_cur[0] = fl_nxt[0], fl_cur[1] = fl_nxt[1];
         fq0 = fq1, fq1 = fq2;
         eq0 = eq1, eq1 = eq2;
-        pc += S, pd += S;
+#if !FDLBM_F32_FSTAGED
+        pc += S;
+#endif
+        pd += S;
         fr_own += Hp, fr_edge += Hp;
         fs_own += Hp >> 5, fs_edge += Hp >> 5;
     }
