@@ -145,6 +145,7 @@ _SIGS = {
     "fdlbm_peer_attach": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int, ctypes.POINTER(PeerInfo)]),
     "fdlbm_pinned_alloc": (ctypes.c_void_p, [ctypes.c_size_t]),
     "fdlbm_pinned_free": (None, [ctypes.c_void_p]),
+    "fdlbm_op_release": (None, []),
     "fdlbm_op_stream": (ctypes.c_int, [ctypes.c_int, ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p]),
     "fdlbm_op_bounce_back": (ctypes.c_int, [ctypes.c_int, ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p,
                                             ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p]),

@@ -194,9 +194,48 @@ __global__ void __launch_bounds__(TPB) k_op_algebra(const __grid_constant__ LbmP
 
 namespace {
 
+// The operator calls run on whole-grid single-slab f64 engines that are KEPT between calls (one per configuration,
+// a few at most): creating an engine per call -- device lattices, page-locked staging, streams -- cost ~50 ms, which
+// made the reference's own loop body, driven call by call through the twins, 25x slower than NumPy.  A call holds the
+// cache lock for its duration (the operators are not re-entrant); an engine whose call failed is dropped.
+struct OpEngines {
+    struct Slot {
+        fdlbm_config cfg;
+        std::vector<double> inlet, outlet;
+        fdlbm_engine *e;
+        uint64_t tick;
+    };
+    std::mutex mu;
+    std::vector<Slot> slots;
+    uint64_t tick = 0;
+};
+inline OpEngines &op_engines()
+{
+    static OpEngines *g = new OpEngines;  // never destroyed: the CUDA runtime may be gone by static-destructor time
+    return *g;
+}
+
 struct TempEngine {
     fdlbm_engine *e = nullptr;
-    ~TempEngine() { fdlbm_destroy(e); }
+    bool keep = false;  // set by the call once it has succeeded
+    std::unique_lock<std::mutex> lock;
+    ~TempEngine()
+    {
+        if (e && !keep) {
+            OpEngines &C = op_engines();
+            for (size_t i = 0; i < C.slots.size(); ++i)
+                if (C.slots[i].e == e) {
+                    C.slots.erase(C.slots.begin() + i);
+                    break;
+                }
+            fdlbm_destroy(e);
+        }
+    }
+    int done(int rc)
+    {
+        keep = rc == 0;
+        return rc;
+    }
 };
 
 // whole-grid single-slab f64 engine for an operator call
@@ -220,8 +259,44 @@ int op_engine(TempEngine &t, const fdlbm_config *cfg_in, int H, int W, bool forc
         c.x_periodic = 1;
         c.zou_he = FDLBM_ZH_NONE;
     }
-    int rc = fdlbm_create(&c, &t.e);
-    return rc;
+    if (c.H <= 0 || c.W <= 0) return fail(FDLBM_E_ARG, "bad grid %d x %d", c.H, c.W);
+    OpEngines &C = op_engines();
+    t.lock = std::unique_lock<std::mutex>(C.mu);
+    // the key: every scalar of the configuration and the CONTENTS of the face profiles
+    fdlbm_config key = c;
+    key.inlet_ux = key.outlet_ux = nullptr;
+    const bool prof = c.zou_he != FDLBM_ZH_NONE && c.inlet_ux && c.outlet_ux;
+    for (auto &s : C.slots) {
+        if (memcmp(&s.cfg, &key, sizeof key) != 0) continue;
+        if (prof && (memcmp(s.inlet.data(), c.inlet_ux, (size_t)c.H * sizeof(double)) != 0 ||
+                     memcmp(s.outlet.data(), c.outlet_ux, (size_t)c.H * sizeof(double)) != 0))
+            continue;
+        s.tick = ++C.tick;
+        t.e = s.e;
+        return 0;
+    }
+    if (C.slots.size() >= 4) {  // drop the least recently used engine
+        size_t lru = 0;
+        for (size_t i = 1; i < C.slots.size(); ++i)
+            if (C.slots[i].tick < C.slots[lru].tick) lru = i;
+        fdlbm_destroy(C.slots[lru].e);
+        C.slots.erase(C.slots.begin() + lru);
+    }
+    fdlbm_engine *e = nullptr;
+    int rc = fdlbm_create(&c, &e);
+    if (rc) return rc;
+    OpEngines::Slot s;
+    memset(&s.cfg, 0, sizeof s.cfg);
+    s.cfg = key;
+    if (prof) {
+        s.inlet.assign(c.inlet_ux, c.inlet_ux + c.H);
+        s.outlet.assign(c.outlet_ux, c.outlet_ux + c.H);
+    }
+    s.e = e;
+    s.tick = ++C.tick;
+    C.slots.push_back(std::move(s));
+    t.e = e;
+    return 0;
 }
 
 int upload_pops(fdlbm_engine *e, int which, const double *f, const double *g)
@@ -253,6 +328,14 @@ int upload_solid(fdlbm_engine *e, const uint8_t *solid)
 
 extern "C" {
 
+void fdlbm_op_release(void)
+{
+    OpEngines &C = op_engines();
+    std::lock_guard<std::mutex> g(C.mu);
+    for (auto &s : C.slots) fdlbm_destroy(s.e);
+    C.slots.clear();
+}
+
 int fdlbm_op_stream(int H, int W, double *f, double *g)
 {
     if (!f || !g) return fail(FDLBM_E_ARG, "null argument");
@@ -266,7 +349,7 @@ int fdlbm_op_stream(int H, int W, double *f, double *g)
     LbmParams<double> P = make_params<double>(e, 0, 0);
     k_op_stream<double><<<cell_grid(e, e->Wl), TPB, 0, e->stream>>>(P);
     CU(cudaGetLastError());
-    return download_pops(e, 1, f, g);
+    return t.done(download_pops(e, 1, f, g));
 }
 
 int fdlbm_op_bounce_back(int H, int W, const uint8_t *reflect, const double *f_behind, const double *g_behind,
@@ -284,7 +367,7 @@ int fdlbm_op_bounce_back(int H, int W, const uint8_t *reflect, const double *f_b
     LbmParams<double> P = make_params<double>(e, 0, 0);
     k_op_bounce_back<double><<<cell_grid(e, e->Wl), TPB, 0, e->stream>>>(P);
     CU(cudaGetLastError());
-    return download_pops(e, 1, f, g);
+    return t.done(download_pops(e, 1, f, g));
 }
 
 int fdlbm_op_stencils(const fdlbm_config *cfg, const double *psi, double *gx, double *gy, double *lap)
@@ -310,7 +393,7 @@ int fdlbm_op_stencils(const fdlbm_config *cfg, const double *psi, double *gx, do
     if ((rc = download_planes<double>(e, gx, 1, 0, e->cfg.W, F.gx, 0, e->Hp))) return rc;
     if ((rc = download_planes<double>(e, gy, 1, 0, e->cfg.W, F.gy, 0, e->Hp))) return rc;
     if ((rc = download_planes<double>(e, lap, 1, 0, e->cfg.W, F.lap, 0, e->Hp))) return rc;
-    return drain_transfers(e);
+    return t.done(drain_transfers(e));
 }
 
 int fdlbm_op_collide(const fdlbm_config *cfg, const uint8_t *solid, const fdlbm_fields *io)
@@ -325,7 +408,7 @@ int fdlbm_op_collide(const fdlbm_config *cfg, const uint8_t *solid, const fdlbm_
     LbmParams<double> P = make_params<double>(e, 1, 0);  // dst = lat[0]
     k_collide_first<double><<<cell_grid(e, e->Wl), TPB, 0, e->stream>>>(P, field_ptrs<double>(e), (const double *)e->psi[0]);
     CU(cudaGetLastError());
-    return download_pops(e, 0, io->f, io->g);
+    return t.done(download_pops(e, 0, io->f, io->g));
 }
 
 int fdlbm_op_collision_terms(const fdlbm_config *cfg, const uint8_t *solid, const fdlbm_fields *in, double *feq,
@@ -345,7 +428,7 @@ int fdlbm_op_collision_terms(const fdlbm_config *cfg, const uint8_t *solid, cons
                                                                     (double *)e->lat[0], (double *)e->lat[1]);
     CU(cudaGetLastError());
     if ((rc = download_pops(e, 0, feq, geq))) return rc;
-    return download_pops(e, 1, F, nullptr);
+    return t.done(download_pops(e, 1, F, nullptr));
 }
 
 int fdlbm_op_algebra(const fdlbm_config *cfg, const fdlbm_fields *in, const fdlbm_algebra_out *out)
@@ -374,7 +457,7 @@ int fdlbm_op_algebra(const fdlbm_config *cfg, const fdlbm_fields *in, const fdlb
     double *srcs[7] = {F.rho, F.ux, F.uy, F.p, F.mu, F.mix_tau, F.gx};
     for (int k = 0; k < 7; ++k)
         if ((rc = download_planes<double>(e, dsts[k], 1, 0, W, srcs[k], 0, Hp))) return rc;
-    return drain_transfers(e);
+    return t.done(drain_transfers(e));
 }
 
 int fdlbm_op_zou_he(const fdlbm_config *cfg, const fdlbm_fields *io)
@@ -391,7 +474,7 @@ int fdlbm_op_zou_he(const fdlbm_config *cfg, const fdlbm_fields *io)
     LbmParams<double> P = make_params<double>(e, 0, 0);  // dst = lat[1], psi_old = psi[0]
     k_op_zou_he<double><<<cell_grid(e, 2), TPB, 0, e->stream>>>(P);
     CU(cudaGetLastError());
-    return download_pops(e, 1, io->f, io->g);
+    return t.done(download_pops(e, 1, io->f, io->g));
 }
 
 int fdlbm_op_moments(const fdlbm_config *cfg, const uint8_t *solid, const fdlbm_fields *io)
@@ -422,7 +505,7 @@ int fdlbm_op_moments(const fdlbm_config *cfg, const uint8_t *solid, const fdlbm_
     double *srcs[9] = {F.rho, F.ux, F.uy, F.p, F.mu, F.mix_tau, F.gx, F.gy, F.lap};
     for (int k = 0; k < 9; ++k)
         if ((rc = download_planes<double>(e, dsts[k], 1, 0, W, srcs[k], 0, Hp))) return rc;
-    return drain_transfers(e);
+    return t.done(drain_transfers(e));
 }
 
 }  // extern "C"

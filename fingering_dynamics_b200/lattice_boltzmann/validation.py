@@ -79,7 +79,7 @@ class Compute(ComputeBase):
         self.mix_tau = self.getMix_tau()
         self.p = self.getP()
         feq, geq, F = self._terms()
-        self.feq, self.geq = feq, geq
+        self.feq, self.geq = feq.copy(), geq.copy()
         self.f, self.g = feq.copy(), geq.copy()
 
     def _fields(self, **extra):
@@ -97,7 +97,7 @@ class Compute(ComputeBase):
         self.p = self.getP()
 
     def updateRho(self):
-        self.rho = self._moments()["rho"]
+        self.rho = self._moments()["rho"].copy()
 
     def updateMu(self):
         self.nabla_psi2 = self.getNabla_psi2()
@@ -105,13 +105,13 @@ class Compute(ComputeBase):
 
     def updateU(self):
         m = self._moments()
-        self.ux, self.uy = m["ux"], m["uy"]
+        self.ux, self.uy = m["ux"].copy(), m["uy"].copy()
 
     def updateF(self):
-        self.f = self._collided()[0]
+        self.f = self._collided("f")[0].copy()
 
     def updateG(self):
-        self.g = self._collided()[1]
+        self.g = self._collided("g")[1].copy()
 
 
 def stream(f, g):

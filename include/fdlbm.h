@@ -183,6 +183,10 @@ void *fdlbm_pinned_alloc(size_t bytes);
 void fdlbm_pinned_free(void *p);
 
 /* ---- stateless operators: NumPy-in / NumPy-out twins of the reference's module functions -------- */
+/* Stateless for the caller: every call takes host arrays and returns host arrays.  Inside, the device buffers of an
+ * operator call are kept for the next call with the same configuration (at most four configurations; a call holds a
+ * process-wide lock, the operators are not re-entrant); fdlbm_op_release frees them. */
+void fdlbm_op_release(void);
 /* stream(f, g), fingering_periodic.py:327-343 (in place, all cells, wrap on both axes) */
 int fdlbm_op_stream(int H, int W, double *f, double *g);
 /* Bounce_back.halfway_bounceback_* / bottom_top_wall with the classes already folded into reflect bits */

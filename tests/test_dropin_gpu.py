@@ -313,3 +313,47 @@ def test_reference_loop_body_verbatim_through_the_va_twin(golden, monkeypatch):
         cm.updateU()
         cm.updateP()
         _check_compute(cm, d, "s%d" % it, mask, skip=("mix_tau", "nabla_psix", "nabla_psiy"))
+
+
+def test_kept_operator_results_follow_in_place_edits(golden, monkeypatch):
+    """The twins keep the last result of each device operator next to copies of its inputs (_compute.py:_memo_*):
+    a getter must see every in-place edit of an input, never hand out an array it keeps, and count device calls
+    the way the loop body needs (one collision call serves the 18 getF / getG calls of an iteration)."""
+    from fingering_dynamics_b200.lattice_boltzmann import fingering_periodic as FP
+    from fingering_dynamics_b200.lattice_boltzmann.create_block import Createblock
+    d = golden("fp_small")
+    monkeypatch.setattr(FP, "H", int(d["H"]))
+    monkeypatch.setattr(FP, "W", int(d["W"]))
+    circles = [((int(c[0]), int(c[1])), int(c[2])) for c in d["circles"]]
+    bpa = Createblock(FP.H, FP.W).setCirleblock(circles)[0]
+    mask = np.logical_not(bpa == 1)
+    cm, fresh = FP.Compute(mask), FP.Compute(mask)
+    a = cm.getfeq(3)
+    a2 = cm.getfeq(3)
+    assert a is not a2 and np.array_equal(a, a2)
+    a2 += 1.0                                              # the caller's array, not the kept one
+    assert np.array_equal(cm.getfeq(3), a)
+    cm.rho[5] *= 1.25                                      # in-place edit of an input
+    fresh.rho = cm.rho.copy()
+    fresh._memo = {}
+    b = cm.getfeq(3)
+    assert not np.array_equal(a, b) and np.array_equal(b, fresh.getfeq(3))
+    monkeypatch.setattr(FP, "tau", FP.tau * 1.5)           # module constants are read at call time
+    fresh._memo = {}
+    assert np.array_equal(cm.getF(2), fresh.getF(2))
+    # one device collision call serves the whole j loop of the body
+    calls = []
+    orig = type(cm)._collided
+
+    def counted(self, which=None, i=None):
+        before = self._memo.get("collide")
+        out = orig(self, which, i)
+        if self._memo.get("collide") is not before:
+            calls.append(1)
+        return out
+    monkeypatch.setattr(type(cm), "_collided", counted)
+    cm._memo.pop("collide", None)
+    for j in range(9):
+        cm.f[j][mask] = cm.getF(j)
+        cm.g[j][mask] = cm.getG(j)
+    assert len(calls) == 1, calls
