@@ -80,6 +80,26 @@ __device__ __forceinline__ void prefetch_l2_bulk(const void *p, unsigned bytes)
 #endif
 
 // ---- bulk asynchronous copies (the TMA engine's 1-D path, cp.async.bulk) completing on an mbarrier ----------
+// solid cell ? psi_wall : s.  In fp64 the plain select compiled to a predicated LDC.64 of the parameter (a 64-bit
+// constant cannot be an instruction operand) whose latency sat in front of the psi shuffles of every column
+// (ncu r2b: 7.5 % of all stall samples on the first consumer); two 32-bit selects take the halves as c[][] operands.
+#ifndef FDLBM_FUSED_PLAIN
+#define FDLBM_FUSED_PLAIN 1  // plain columns run a body without the domain / Zou-He tests, the faces get their own CTAs; 0 for A/B
+#endif
+#ifndef FDLBM_WALL_SEL
+#define FDLBM_WALL_SEL 1
+#endif
+__device__ __forceinline__ float pick_wall(unsigned solid, const float &wall, float s) { return solid ? wall : s; }
+__device__ __forceinline__ double pick_wall(unsigned solid, const double &wall, double s)
+{
+#if FDLBM_WALL_SEL
+    const int lo = solid ? __double2loint(wall) : __double2loint(s);
+    const int hi = solid ? __double2hiint(wall) : __double2hiint(s);
+    return __hiloint2double(hi, lo);
+#else
+    return solid ? wall : s;
+#endif
+}
 __device__ __forceinline__ unsigned smem_u32(const void *p) { return (unsigned)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ void mbar_init(void *bar, unsigned count)
 {
@@ -182,8 +202,11 @@ struct RawFlags {
 
 // HPC > 0: the row pitch Hp is the compile-time constant HPC (all population offsets become immediates of the
 // loads / stores / cp.async); HPC == 0: Hp is read from the parameters (any grid height).
-template <typename T, int TY, int HPC>
-__global__ void __launch_bounds__(TY, sizeof(T) == 8 ? FDLBM_FUSED_MINB64 : FDLBM_FUSED_MINB32) k_fused(const __grid_constant__ LbmParams<T> P, int nyt, int chunk)
+// PLAIN: every column the strip touches (xs-1 .. xe+1) is inside the domain and carries no Zou-He rule, so the
+// per-column domain / face tests (and the loads of W, gx0, psi_left, psi_right they need: 24 LDC per warp and column
+// in the one-body kernel) are compiled out; the face columns run the general body in their own small CTAs.
+template <typename T, int TY, int HPC, bool PLAIN>
+__device__ __forceinline__ void fused_strip(const LbmParams<T> &P, const int yt, const int xs, const int xe)
 {
     using C = FusedCfg<T, TY>;
     constexpr int D = FUSED_D, NS = C::NS, PT = C::PT, HALO = C::HALO, FAM = C::FAM;
@@ -200,9 +223,6 @@ __global__ void __launch_bounds__(TY, sizeof(T) == 8 ? FDLBM_FUSED_MINB64 : FDLB
     // its slowest SM, ~5 % after the median one) by measured chunk lengths or by placement was tried three ways in
     // round 2 and lost 2-5 % every time (profiles/README.md, profiles/r2/tail_experiments/): anything that pulls the
     // strips of a chunk out of lock step costs more in L2 / DRAM locality than the tail it removes.
-    const int yt = blockIdx.x % nyt;
-    const int ck = blockIdx.x / nyt;
-    const int xs = ck * chunk, xe = min(P.Wl, xs + chunk);
     const int y0 = yt * TY;
     const int y = y0 + t;
     const int ny = min(TY, H - y0);
@@ -223,7 +243,7 @@ __global__ void __launch_bounds__(TY, sizeof(T) == 8 ? FDLBM_FUSED_MINB64 : FDLB
     const int ye2 = wrap_row(y + 1), je2 = j + 1;  // second neighbour of a one-row warp (edge2)
 
     auto slot = [](int c) { return (NS & (NS - 1)) == 0 ? (c & (NS - 1)) : ((c % NS) + NS) % NS; };
-    auto in_domain = [&](int c) { return P.x_periodic || (P.gx0 + c >= 0 && P.gx0 + c < P.W); };
+    auto in_domain = [&](int c) { return PLAIN || P.x_periodic || (P.gx0 + c >= 0 && P.gx0 + c < P.W); };
 
     // Interior strips (no y wrap inside the apron) fill their g stages with BULK asynchronous copies: one thread
     // issues 9 cp.async.bulk of a whole stage row each (1056 bytes), completion is counted in bytes on the stage's
@@ -307,15 +327,20 @@ __global__ void __launch_bounds__(TY, sizeof(T) == 8 ? FDLBM_FUSED_MINB64 : FDLB
     // psi_new of the cell (column c, global row yy >= 0 already wrapped, stage row jj) from the g stages
     auto psi_staged = [&](int c, int yy, int jj, unsigned flags, T g[9]) -> T {
         if (yy < 0) return P.psi_wall;
-        const int gx = P.gx0 + c;
-        if (!P.x_periodic) {
-            if (gx < 0) return P.psi_left;
-            if (gx >= P.W) return P.psi_right;
+        if (!PLAIN) {
+            const int gx = P.gx0 + c;
+            if (!P.x_periodic) {
+                if (gx < 0) return P.psi_left;
+                if (gx >= P.W) return P.psi_right;
+            }
         }
         pull_staged<T, PT>(gst + slot(c - 1) * FAM, gst + slot(c) * FAM, gst + slot(c + 1) * FAM, jj, flags & 0xffu, g);
-        if (P.zou_he && (gx == 0 || gx == P.W - 1)) zou_he_g(P, gx, yy, g);
-        if (flags & 0x100u) return P.psi_wall;
-        return (((g[0] + g[1]) + (g[2] + g[3])) + ((g[4] + g[5]) + (g[6] + g[7]))) + g[8];
+        if (!PLAIN && P.zou_he) {
+            const int gx = P.gx0 + c;
+            if (gx == 0 || gx == P.W - 1) zou_he_g(P, gx, yy, g);
+        }
+        const T s = (((g[0] + g[1]) + (g[2] + g[3])) + ((g[4] + g[5]) + (g[6] + g[7]))) + g[8];
+        return pick_wall(flags & 0x100u, P.psi_wall, s);
     };
     // psi_new of column c on rows y-1, y, y+1 (q_m, q_0, q_p); the pulled g of the own cell is returned
     auto psi_column = [&](int c, unsigned fl_own, unsigned fl_edge, T g[9], T &q_m, T &q_0, T &q_p) {
@@ -404,7 +429,7 @@ __global__ void __launch_bounds__(TY, sizeof(T) == 8 ? FDLBM_FUSED_MINB64 : FDLB
         const RawFlags eq2 = edge ? load_flags(x + 3, ye1) : z;
         psi_column(x + 1, fl_nxt, fe_nxt, g_nxt, pp_m, pp_0, pp_p);
         if (active) {
-            if (P.zou_he) {
+            if (!PLAIN && P.zou_he) {
                 const int gx_ = P.gx0 + x;
                 if (gx_ == 0 || gx_ == P.W - 1) zou_he_f(P, x, gx_, y, f, PullRow<T>());
             }
@@ -417,7 +442,7 @@ __global__ void __launch_bounds__(TY, sizeof(T) == 8 ? FDLBM_FUSED_MINB64 : FDLB
                 collide(P, m, f, g_cur);
             }
             store_cell_hp(P, Hp, x, y, f, g_cur);
-            if (P.zou_he) {  // the next step's Zou-He needs grad psi and mu at the face columns
+            if (!PLAIN && P.zou_he) {  // the next step's Zou-He needs grad psi and mu at the face columns
                 const int gx_ = P.gx0 + x;
                 if (gx_ < 2 || gx_ >= P.W - 2) P.psi_new[cell_idx(Hp, x, y)] = p0_0;
             }
@@ -431,6 +456,42 @@ __global__ void __launch_bounds__(TY, sizeof(T) == 8 ? FDLBM_FUSED_MINB64 : FDLB
         eq0 = eq1, eq1 = eq2;
     }
     cp_async_wait<0>();
+}
+
+// The launch grid (same scheme as f32p::k_fused_f32p): `n_fast` CTAs march over the plain columns [fx0, fx1) (strip =
+// blockIdx % nyt, chunks of `chunk` columns) with the PLAIN body, followed by the FACE CTAs -- one per strip and side for
+// the columns next to the Zou-He faces / the domain edge, [0, fx0) and [fx1, Wl) -- with the general body.  Face CTAs
+// come last in dispatch order and are tiny (2-3 columns): they slip into the CTA slots the one-wave chunking leaves free.
+template <typename T, int TY, int HPC>
+__global__ void __launch_bounds__(TY, sizeof(T) == 8 ? FDLBM_FUSED_MINB64 : FDLBM_FUSED_MINB32)
+    k_fused(const __grid_constant__ LbmParams<T> P, int nyt, int chunk, int fx0, int fx1, int n_fast)
+{
+    if ((int)blockIdx.x >= n_fast) {  // face CTA
+        const int k = (int)blockIdx.x - n_fast, side = k / nyt;
+        const bool left = fx0 > 0 && side == 0;
+        fused_strip<T, TY, HPC, false>(P, k % nyt, left ? 0 : fx1, left ? fx0 : P.Wl);
+        return;
+    }
+    const int xs = fx0 + ((int)blockIdx.x / nyt) * chunk;
+#if FDLBM_FUSED_PLAIN
+    fused_strip<T, TY, HPC, true>(P, (int)blockIdx.x % nyt, xs, min(fx1, xs + chunk));
+#else
+    fused_strip<T, TY, HPC, false>(P, (int)blockIdx.x % nyt, xs, min(fx1, xs + chunk));
+#endif
+}
+
+// the plain column range of this slab: columns x with x-1 .. x+2 inside the domain and away from the Zou-He faces and
+// their neighbours (where psi_new is stored for the next step's Zou-He); everything on an x-periodic grid
+template <typename T>
+inline void fused_plain_range(const LbmParams<T> &P, int &fx0, int &fx1)
+{
+    fx0 = 0, fx1 = P.Wl;
+    if (FDLBM_FUSED_PLAIN && !P.x_periodic) {
+        fx0 = 2 - P.gx0 > 0 ? 2 - P.gx0 : 0;
+        fx1 = P.W - 3 - P.gx0 < P.Wl ? P.W - 3 - P.gx0 : P.Wl;
+        if (fx0 > P.Wl) fx0 = P.Wl;
+        if (fx1 < fx0) fx1 = fx0;
+    }
 }
 
 // Column chunk length for `nyt` strips on `n_cta` resident CTA slots.  With c chunks per strip the kernel takes
@@ -481,9 +542,17 @@ int launch_fused_hp(const LbmParams<T> &P, cudaStream_t stream)
     }
     // column chunks per strip, all strips of a chunk in step (strips are the fast CTA index)
     const int nyt = (P.H + FUSED_TY - 1) / FUSED_TY;
-    const int chunk = fused_chunk(nyt, n_cta, P.Wl);
-    const int nchunks = (P.Wl + chunk - 1) / chunk;
-    kern<<<nyt * nchunks, FUSED_TY, C::SMEM, stream>>>(P, nyt, chunk);
+    int fx0, fx1;
+    fused_plain_range(P, fx0, fx1);
+    const int n_face = nyt * ((fx0 > 0) + (fx1 < P.Wl));
+    // one wave of plain-column CTAs; keep a slot free for the face CTAs to slip into
+    const int slots = n_face && n_cta > nyt ? n_cta - 1 : n_cta;
+    int chunk = 8, nchunks = 0;
+    if (fx1 > fx0) {
+        chunk = fused_chunk(nyt, slots, fx1 - fx0);
+        nchunks = (fx1 - fx0 + chunk - 1) / chunk;
+    }
+    kern<<<nyt * nchunks + n_face, FUSED_TY, C::SMEM, stream>>>(P, nyt, chunk, fx0, fx1, nyt * nchunks);
     return 0;
 }
 

@@ -41,6 +41,18 @@ namespace fdlbm {
 #ifndef FDLBM_F32_FSTAGED
 #define FDLBM_F32_FSTAGED 1  // the f columns go through a second stage ring (measured +1.5 %); 0: per-thread global loads behind an L2 prefetch
 #endif
+// Sizing experiment for a two-steps-per-pass kernel, never on in the shipped build:
+// FDLBM_F32_MOCK2 = 1 runs the arithmetic of a SECOND step on every column -- f and g pulled from the stages again,
+// psi column, stencils, moments, collision, one more barrier -- and folds its results, scaled by a run-time zero, into
+// the psi carry, so the memory traffic of the pass is unchanged and only the per-warp instruction chain doubles;
+// FDLBM_F32_PADSMEM = bytes of unused shared memory per CTA (what the step-t+1 rings would take: fewer CTAs per SM).
+// 2 x LU / (time of that pass) bounds what temporal blocking can reach from above.
+#ifndef FDLBM_F32_MOCK2
+#define FDLBM_F32_MOCK2 0
+#endif
+#ifndef FDLBM_F32_PADSMEM
+#define FDLBM_F32_PADSMEM 0
+#endif
 namespace f32p {
 
 typedef float2 p2;
@@ -96,7 +108,7 @@ FDLBM_DI float lds_f(const float *p)
 struct Cfg {
     static constexpr int NT = 128, ROWS = 256, HALO = 4, PT = ROWS + 2 * HALO, NS = 4, FAM = 9 * PT;
     static constexpr int RINGS = FDLBM_F32_FSTAGED ? 2 : 1;  // g ring (+ f ring)
-    static constexpr size_t SMEM = (size_t)RINGS * NS * FAM * sizeof(float);
+    static constexpr size_t SMEM = (size_t)RINGS * NS * FAM * sizeof(float) + FDLBM_F32_PADSMEM;
 };
 
 // moments of the cell pair (fingering_periodic.py:123-152, 201-208), packed; see moments() in lbm_device.cuh
@@ -198,7 +210,7 @@ FDLBM_DI void collide2(const LbmParams<float> &P, const Macro2 &m, bool solid0, 
 // order and are tiny (2-3 columns): they slip into the CTA slots the one-wave chunking leaves free.
 // HPC > 0: compile-time row pitch (every population offset is an immediate); HPC == 0: P.Hp
 template <int HPC>
-__global__ void __launch_bounds__(Cfg::NT, 3)
+__global__ void __launch_bounds__(Cfg::NT, FDLBM_F32_PADSMEM > 36000 ? 2 : 3)
     k_fused_f32p(const __grid_constant__ LbmParams<float> P, int nyt, int chunk, int fx0, int fx1, int n_fast)
 {
     typedef float T;
@@ -574,6 +586,36 @@ __global__ void __launch_bounds__(Cfg::NT, 3)
                 }
             }
         }
+#if FDLBM_F32_MOCK2
+        {   // the arithmetic of a second step on this column (see FDLBM_F32_MOCK2 above); results scaled by zero
+            __syncthreads();  // a real second stage reads what the neighbours' first stage has just written
+            asm volatile("" ::: "memory");
+            const p2 zero = bc((float)(P.gx0 < -1000000));
+            p2 f2[9], g2[9], q2;
+            T q2_lo, q2_hi;
+            const unsigned b0bits = fl_cur[0] & 0xffu, b1bits = fl_cur[1] & 0xffu;
+            const bool anyb = __any_sync(FULL, has && ((b0bits | b1bits) != 0u));
+            unsigned fe2 = fe_nxt;
+            asm volatile("" : "+r"(fe2));
+            psi_column(x, fe2, fl_cur, g2, q2, q2_lo, q2_hi);
+            if (has) {
+                pull_pair(fst, x, b0bits, b1bits, anyb, f2);
+                const bool s0 = fl_cur[0] & 0x100u, s1 = fl_cur[1] & 0x100u;
+                if (!(s0 && s1)) {
+                    T gxa, gya, lapa, gxb, gyb, lapb;
+                    stencil9(q2.x, pp.x, pm.x, q2.y, q2_lo, pp.y, pm.y, pm_lo, pp_lo, gxa, gya, lapa);
+                    stencil9(q2.y, pp.y, pm.y, q2_hi, q2.x, pp_hi, pm_hi, pm.x, pp.x, gxb, gyb, lapb);
+                    Macro2 m2;
+                    moments2(P, f2, q2, mk(gxa, gxb), mk(gya, gyb), mk(lapa, lapb), s0, s1, m2);
+                    collide2(P, m2, s0, s1, f2, g2);
+                }
+                p2 acc = mk(0.0f, 0.0f);
+#pragma unroll
+                for (int i = 0; i < 9; ++i) acc = add(acc, add(f2[i], g2[i]));  // stands in for the 18 stage stores
+                pp = fma2(acc, zero, pp);
+            }
+        }
+#endif
         {   // g of column x+1 for the next iteration's collision (the stages x .. x+2 are still in place)
             const unsigned b0bits = fl_nxt[0] & 0xffu, b1bits = fl_nxt[1] & 0xffu;
             const bool anyb = __any_sync(FULL, has && ((b0bits | b1bits) != 0u));

@@ -56,3 +56,12 @@ for _ in range(n):
     fb = copy.deepcopy(cm.f); gb = copy.deepcopy(cm.g)
 dh = (time.perf_counter() - t0) / n
 print("  of which the body's own host statements (18 masked assignments + 2 deepcopies): %.1f ms" % (dh * 1e3))
+
+if os.environ.get("VL_PROFILE"):
+    import cProfile, pstats
+    pr = cProfile.Profile()
+    pr.enable()
+    for _ in range(3):
+        iteration()
+    pr.disable()
+    pstats.Stats(pr).sort_stats("cumulative").print_stats(22)

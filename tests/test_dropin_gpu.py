@@ -333,8 +333,9 @@ def test_kept_operator_results_follow_in_place_edits(golden, monkeypatch):
     assert a is not a2 and np.array_equal(a, a2)
     a2 += 1.0                                              # the caller's array, not the kept one
     assert np.array_equal(cm.getfeq(3), a)
-    cm.rho[5] *= 1.25                                      # in-place edit of an input
-    fresh.rho = cm.rho.copy()
+    cm.rho[5] *= 1.25                                      # in-place edits of two inputs (at u = 0 only p enters f_eq,3)
+    cm.p[5] *= 1.25
+    fresh.rho, fresh.p = cm.rho.copy(), cm.p.copy()
     fresh._memo = {}
     b = cm.getfeq(3)
     assert not np.array_equal(a, b) and np.array_equal(b, fresh.getfeq(3))
