@@ -242,7 +242,9 @@ __device__ __forceinline__ void fused_strip(const LbmParams<T> &P, const int yt,
     const int ye1 = wrap_row(edge_lo ? y - 1 : y + 1), je1 = edge_lo ? j - 1 : j + 1;
     const int ye2 = wrap_row(y + 1), je2 = j + 1;  // second neighbour of a one-row warp (edge2)
 
-    auto slot = [](int c) { return (NS & (NS - 1)) == 0 ? (c & (NS - 1)) : ((c % NS) + NS) % NS; };
+    // the stage of column c, counted from the strip's first column
+    auto slot = [xs](int c) { return (NS & (NS - 1)) == 0 ? ((c - xs) & (NS - 1)) : (((c - xs) % NS) + NS) % NS; };
+    auto slot_add = [](int sc, int d) { return (NS & (NS - 1)) == 0 ? ((sc + d) & (NS - 1)) : (((sc + d) % NS) + NS) % NS; };
     auto in_domain = [&](int c) { return PLAIN || P.x_periodic || (P.gx0 + c >= 0 && P.gx0 + c < P.W); };
 
     // Interior strips (no y wrap inside the apron) fill their g stages with BULK asynchronous copies: one thread
@@ -263,13 +265,13 @@ __device__ __forceinline__ void fused_strip(const LbmParams<T> &P, const int yt,
     // one pipeline step: g column v+2+D (and, FDLBM_F_STAGED, f column v+1+D: f is consumed one column behind g, so
     // its ring holds x-1..x+1 plus the column in flight); only columns this run reads.  Whenever an f column is
     // fetched a g column is fetched with it, on the same mbarrier / commit group.
-    auto prefetch = [&](int v) {
+    auto prefetch_s = [&](int v, const int scg) {  // scg = slot(v + 2 + D)
         const int cg = v + 2 + D;
         if (cg >= xs - 2 && cg <= xe + 1) {
-            T *stage = gst + slot(cg) * FAM;
+            T *stage = gst + scg * FAM;
             const T *col = P.src + lat_idx(Hp, cg, 9, 0);
             const bool with_f = FDLBM_F_STAGED && cg - 1 >= xs - 1 && cg - 1 <= xe;
-            T *fstage = fst + slot(cg - 1) * FAM;
+            T *fstage = fst + slot_add(scg, -1) * FAM;
             const T *fcol = P.src + lat_idx(Hp, cg - 1, 0, 0);
             if (bulk) {
                 // one bulk copy per population for the contiguous piece of the stage row ...
@@ -277,14 +279,14 @@ __device__ __forceinline__ void fused_strip(const LbmParams<T> &P, const int yt,
                     const int r0 = wrap_lo ? y0 : y0 - HALO;               // its first row
                     const int r1 = wrap_hi ? y0 + ny : y0 + ny + HALO;     // one past its last row
                     const unsigned bytes = (unsigned)((r1 - r0) * sizeof(T));
-                    mbar_expect_tx(&bars[slot(cg)], (with_f ? 18u : 9u) * bytes);
+                    mbar_expect_tx(&bars[scg], (with_f ? 18u : 9u) * bytes);
 #pragma unroll
                     for (int pop = 0; pop < 9; ++pop)
-                        bulk_g2s(stage + pop * PT + (r0 - (y0 - HALO)), col + (size_t)pop * Hp + r0, bytes, &bars[slot(cg)]);
+                        bulk_g2s(stage + pop * PT + (r0 - (y0 - HALO)), col + (size_t)pop * Hp + r0, bytes, &bars[scg]);
                     if (with_f) {
 #pragma unroll
                         for (int pop = 0; pop < 9; ++pop)
-                            bulk_g2s(fstage + pop * PT + (r0 - (y0 - HALO)), fcol + (size_t)pop * Hp + r0, bytes, &bars[slot(cg)]);
+                            bulk_g2s(fstage + pop * PT + (r0 - (y0 - HALO)), fcol + (size_t)pop * Hp + r0, bytes, &bars[scg]);
                     }
                 }
                 // ... and one 16-byte cp.async per population for an apron that wraps in y (16-byte bulk copies
@@ -306,11 +308,13 @@ __device__ __forceinline__ void fused_strip(const LbmParams<T> &P, const int yt,
         }
         cp_async_commit();
     };
+    auto prefetch = [&](int v) { prefetch_s(v, slot(v + 2 + D)); };
     // wait until g column c has landed in its stage (bulk path: the fill of column c is the
     // ((c - (xs-2)) / NS)-th use of its mbarrier, whose parity is waited for)
-    auto landed = [&](int c) {
-        if (bulk) mbar_wait(&bars[slot(c)], (unsigned)(((c - (xs - 2)) / NS) & 1));
+    auto landed_s = [&](int c, const int sc) {
+        if (bulk) mbar_wait(&bars[sc], (unsigned)(((c - (xs - 2)) / NS) & 1));
     };
+    auto landed = [&](int c) { landed_s(c, slot(c)); };
     // Per-cell flags are plain global loads issued two columns ahead of their use and carried RAW in
     // registers: nothing depends on them until they are decoded two iterations later, so their latency
     // never sits on the critical path.
@@ -325,7 +329,7 @@ __device__ __forceinline__ void fused_strip(const LbmParams<T> &P, const int yt,
         return r.refl | (((r.word >> (yy & 31)) & 1u) << 8);
     };
     // psi_new of the cell (column c, global row yy >= 0 already wrapped, stage row jj) from the g stages
-    auto psi_staged = [&](int c, int yy, int jj, unsigned flags, T g[9]) -> T {
+    auto psi_staged = [&](int c, const int sc, int yy, int jj, unsigned flags, T g[9]) -> T {  // sc = slot(c)
         if (yy < 0) return P.psi_wall;
         if (!PLAIN) {
             const int gx = P.gx0 + c;
@@ -334,7 +338,7 @@ __device__ __forceinline__ void fused_strip(const LbmParams<T> &P, const int yt,
                 if (gx >= P.W) return P.psi_right;
             }
         }
-        pull_staged<T, PT>(gst + slot(c - 1) * FAM, gst + slot(c) * FAM, gst + slot(c + 1) * FAM, jj, flags & 0xffu, g);
+        pull_staged<T, PT>(gst + slot_add(sc, -1) * FAM, gst + sc * FAM, gst + slot_add(sc, 1) * FAM, jj, flags & 0xffu, g);
         if (!PLAIN && P.zou_he) {
             const int gx = P.gx0 + c;
             if (gx == 0 || gx == P.W - 1) zou_he_g(P, gx, yy, g);
@@ -343,21 +347,21 @@ __device__ __forceinline__ void fused_strip(const LbmParams<T> &P, const int yt,
         return pick_wall(flags & 0x100u, P.psi_wall, s);
     };
     // psi_new of column c on rows y-1, y, y+1 (q_m, q_0, q_p); the pulled g of the own cell is returned
-    auto psi_column = [&](int c, unsigned fl_own, unsigned fl_edge, T g[9], T &q_m, T &q_0, T &q_p) {
+    auto psi_column = [&](int c, const int sc, unsigned fl_own, unsigned fl_edge, T g[9], T &q_m, T &q_0, T &q_p) {
         q_0 = T(0);
-        if (active) q_0 = psi_staged(c, y, j, fl_own, g);
+        if (active) q_0 = psi_staged(c, sc, y, j, fl_own, g);
         T e1 = T(0), e2 = T(0);
         if (edge) {
             T gh[9];
-            e1 = psi_staged(c, ye1, je1, fl_edge, gh);
-            if (edge2) e2 = psi_staged(c, ye2, je2, decode(load_flags(c, ye2), ye2), gh);
+            e1 = psi_staged(c, sc, ye1, je1, fl_edge, gh);
+            if (edge2) e2 = psi_staged(c, sc, ye2, je2, decode(load_flags(c, ye2), ye2), gh);
         }
         const T dn = __shfl_up_sync(FULL, q_0, 1), up = __shfl_down_sync(FULL, q_0, 1);
         q_m = edge_lo ? e1 : dn;
         q_p = edge_hi ? (edge_lo ? e2 : e1) : up;
     };
 
-    T g_cur[9], g_nxt[9];
+    T g_a[9], g_b[9];  // g of columns x and x+1 (roles alternate in the unrolled loop)
     T pm_m, pm_0, pm_p, p0_m, p0_0, p0_p, pp_m, pp_0, pp_p;  // psi_new on columns x-1, x, x+1 x rows y-1, y, y+1
     unsigned fl_cur = 0, fl_nxt = 0;                          // flags of this thread's cell in columns x, x+1
     const RawFlags z{0u, 0u};
@@ -381,18 +385,22 @@ __device__ __forceinline__ void fused_strip(const LbmParams<T> &P, const int yt,
     landed(xs - 1);
     landed(xs);
     __syncthreads();
-    psi_column(xs - 1, decode(rf_m1, y), decode(re_m1, ye1), g_nxt, pm_m, pm_0, pm_p);
+    psi_column(xs - 1, slot(xs - 1), decode(rf_m1, y), decode(re_m1, ye1), g_b, pm_m, pm_0, pm_p);
     __syncthreads();
     prefetch(xs - 1);
     cp_async_wait<D>();  // g column xs+1 has landed
     landed(xs + 1);
     __syncthreads();
     fl_cur = decode(rf_0, y);
-    psi_column(xs, fl_cur, decode(re_0, ye1), g_cur, p0_m, p0_0, p0_p);
+    psi_column(xs, slot(xs), fl_cur, decode(re_0, ye1), g_a, p0_m, p0_0, p0_p);
 
-    for (int x = xs; x < xe; ++x) {
+    // one column.  sx = slot(x); g_cur = g of column x (in), g_nxt = g of column x+1 (out).  Unrolling this loop was
+    // measured on B200 (profiles/r2/r2_ab_unroll.txt, r2_ab_lean1.txt): by 4 with every stage slot a literal -18 % (four
+    // copies of the 12 KB body overflow the 32 KB instruction cache level), by 2 (no register moves for g) -2 %; running
+    // pointers for the flag loads / stores instead of index arithmetic: -0.3 % (r2_ab_lean2.txt).
+    auto column = [&](const int x, const int sx, T (&g_cur)[9], T (&g_nxt)[9]) {
         cp_async_wait<D - 1>();  // g column x+2 has landed
-        landed(x + 2);
+        landed_s(x + 2, slot_add(sx, 2));
         __syncthreads();         // ... for every thread; and everybody is done with iteration x-1
         // Decode the flags of column x+1 BEFORE any new global load is issued: they were loaded two iterations
         // ago, but the hardware scoreboard slots are shared -- decoding them after this iteration's f loads
@@ -400,13 +408,13 @@ __device__ __forceinline__ void fused_strip(const LbmParams<T> &P, const int yt,
         fl_nxt = decode(fq0, y);
         unsigned fe_nxt = decode(eq0, ye1);
         asm volatile("" : "+r"(fl_nxt), "+r"(fe_nxt)::"memory");
-        prefetch(x);             // overwrites the stage of g column x-1: no longer read
+        prefetch_s(x, slot_add(sx, 2 + D));  // overwrites the stage of g column x-1: no longer read
         T f[9];
         {
             // f of column x straight into registers; consumed after the psi phase below
 #if FDLBM_F_STAGED
             if (active)
-                pull_staged<T, PT>(fst + slot(x - 1) * FAM, fst + slot(x) * FAM, fst + slot(x + 1) * FAM, j, fl_cur & 0xffu, f);
+                pull_staged<T, PT>(fst + slot_add(sx, -1) * FAM, fst + sx * FAM, fst + slot_add(sx, 1) * FAM, j, fl_cur & 0xffu, f);
 #else
             if (active) pull_hp(P, Hp, x, y, 0, fl_cur & 0xffu, f);
 #endif
@@ -427,7 +435,7 @@ __device__ __forceinline__ void fused_strip(const LbmParams<T> &P, const int yt,
         }
         const RawFlags fq2 = active ? load_flags(x + 3, y) : z;  // decoded two iterations from now
         const RawFlags eq2 = edge ? load_flags(x + 3, ye1) : z;
-        psi_column(x + 1, fl_nxt, fe_nxt, g_nxt, pp_m, pp_0, pp_p);
+        psi_column(x + 1, slot_add(sx, 1), fl_nxt, fe_nxt, g_nxt, pp_m, pp_0, pp_p);
         if (active) {
             if (!PLAIN && P.zou_he) {
                 const int gx_ = P.gx0 + x;
@@ -447,13 +455,16 @@ __device__ __forceinline__ void fused_strip(const LbmParams<T> &P, const int yt,
                 if (gx_ < 2 || gx_ >= P.W - 2) P.psi_new[cell_idx(Hp, x, y)] = p0_0;
             }
         }
-#pragma unroll
-        for (int i = 0; i < 9; ++i) g_cur[i] = g_nxt[i];
         pm_m = p0_m, pm_0 = p0_0, pm_p = p0_p;
         p0_m = pp_m, p0_0 = pp_0, p0_p = pp_p;
         fl_cur = fl_nxt;
         fq0 = fq1, fq1 = fq2;
         eq0 = eq1, eq1 = eq2;
+    };
+    for (int x = xs; x < xe; ++x) {
+        column(x, slot(x), g_a, g_b);
+#pragma unroll
+        for (int i = 0; i < 9; ++i) g_a[i] = g_b[i];
     }
     cp_async_wait<0>();
 }
@@ -560,7 +571,7 @@ int launch_fused_hp(const LbmParams<T> &P, cudaStream_t stream)
 template <typename T>
 int launch_fused(const LbmParams<T> &P, cudaStream_t stream)
 {
-#ifdef FDLBM_HP_SPECIALISATION  // measured on B200: no gain (19.88 vs 19.93 GLUPS), so off by default
+#ifndef FDLBM_NO_HP_SPECIALISATION  // +2.1 .. 2.6 % with the PLAIN body (profiles/r2/r2_ab_lean1.txt; it was +-0 before the split)
     switch (P.Hp) {
     case 2048: return launch_fused_hp<T, 2048>(P, stream);
     case 4096: return launch_fused_hp<T, 4096>(P, stream);
