@@ -86,6 +86,9 @@ __device__ __forceinline__ void prefetch_l2_bulk(const void *p, unsigned bytes)
 #ifndef FDLBM_FUSED_PLAIN
 #define FDLBM_FUSED_PLAIN 1  // plain columns run a body without the domain / Zou-He tests, the faces get their own CTAs; 0 for A/B
 #endif
+#ifndef FDLBM_EDGE2_IN_PLAIN
+#define FDLBM_EDGE2_IN_PLAIN 0  // 1 for A/B only: the PLAIN body keeps the in-loop flag load of one-row warps (see edge2 below)
+#endif
 #ifndef FDLBM_WALL_SEL
 #define FDLBM_WALL_SEL 1
 #endif
@@ -234,7 +237,11 @@ __device__ __forceinline__ void fused_strip(const LbmParams<T> &P, const int yt,
     // staged data, one extra pull for two lanes per warp), so warps never wait for each other.
     const bool edge_lo = active && lane == 0;
     const bool edge_hi = active && (lane == 31 || t == ny - 1);
-    const bool edge = edge_lo || edge_hi, edge2 = edge_lo && edge_hi;
+    // A lane that is both (a warp of ONE active row: H % 32 == 1 only) needs a second neighbour row, whose flags it
+    // loads in the loop.  The PLAIN body is only launched when no warp is like that and has no such load: ptxas put it
+    // on the scoreboard of the look-ahead flag loads and then made the psi shuffles -- which reuse its register --
+    // wait for that scoreboard on EVERY path: a full memory latency per column (ncu r2c: 14 % of all stall samples).
+    const bool edge = edge_lo || edge_hi, edge2 = (!PLAIN || FDLBM_EDGE2_IN_PLAIN) && edge_lo && edge_hi;
     auto wrap_row = [&](int yy) {  // wrapped global row, or -1 for a ghost row of a y-wall variant
         if (yy < 0 || yy >= H) return P.y_wall ? -1 : (yy < 0 ? yy + H : yy - H);
         return yy;
@@ -475,20 +482,21 @@ __device__ __forceinline__ void fused_strip(const LbmParams<T> &P, const int yt,
 // come last in dispatch order and are tiny (2-3 columns): they slip into the CTA slots the one-wave chunking leaves free.
 template <typename T, int TY, int HPC>
 __global__ void __launch_bounds__(TY, sizeof(T) == 8 ? FDLBM_FUSED_MINB64 : FDLBM_FUSED_MINB32)
-    k_fused(const __grid_constant__ LbmParams<T> P, int nyt, int chunk, int fx0, int fx1, int n_fast)
+    k_fused(const __grid_constant__ LbmParams<T> P, int nyt, int chunk, int fx0, int fx1, int n_fast, int plain_ok)
 {
-    if ((int)blockIdx.x >= n_fast) {  // face CTA
+    int yt, xs, xe;
+    const bool face = (int)blockIdx.x >= n_fast;
+    if (face) {
         const int k = (int)blockIdx.x - n_fast, side = k / nyt;
         const bool left = fx0 > 0 && side == 0;
-        fused_strip<T, TY, HPC, false>(P, k % nyt, left ? 0 : fx1, left ? fx0 : P.Wl);
-        return;
+        yt = k % nyt, xs = left ? 0 : fx1, xe = left ? fx0 : P.Wl;
+    } else {
+        yt = (int)blockIdx.x % nyt, xs = fx0 + ((int)blockIdx.x / nyt) * chunk, xe = min(fx1, xs + chunk);
     }
-    const int xs = fx0 + ((int)blockIdx.x / nyt) * chunk;
-#if FDLBM_FUSED_PLAIN
-    fused_strip<T, TY, HPC, true>(P, (int)blockIdx.x % nyt, xs, min(fx1, xs + chunk));
-#else
-    fused_strip<T, TY, HPC, false>(P, (int)blockIdx.x % nyt, xs, min(fx1, xs + chunk));
-#endif
+    if (FDLBM_FUSED_PLAIN && plain_ok && !face)
+        fused_strip<T, TY, HPC, true>(P, yt, xs, xe);
+    else
+        fused_strip<T, TY, HPC, false>(P, yt, xs, xe);
 }
 
 // the plain column range of this slab: columns x with x-1 .. x+2 inside the domain and away from the Zou-He faces and
@@ -497,7 +505,7 @@ template <typename T>
 inline void fused_plain_range(const LbmParams<T> &P, int &fx0, int &fx1)
 {
     fx0 = 0, fx1 = P.Wl;
-    if (FDLBM_FUSED_PLAIN && !P.x_periodic) {
+    if (FDLBM_FUSED_PLAIN && P.H % 32 != 1 && !P.x_periodic) {
         fx0 = 2 - P.gx0 > 0 ? 2 - P.gx0 : 0;
         fx1 = P.W - 3 - P.gx0 < P.Wl ? P.W - 3 - P.gx0 : P.Wl;
         if (fx0 > P.Wl) fx0 = P.Wl;
@@ -563,7 +571,7 @@ int launch_fused_hp(const LbmParams<T> &P, cudaStream_t stream)
         chunk = fused_chunk(nyt, slots, fx1 - fx0);
         nchunks = (fx1 - fx0 + chunk - 1) / chunk;
     }
-    kern<<<nyt * nchunks + n_face, FUSED_TY, C::SMEM, stream>>>(P, nyt, chunk, fx0, fx1, nyt * nchunks);
+    kern<<<nyt * nchunks + n_face, FUSED_TY, C::SMEM, stream>>>(P, nyt, chunk, fx0, fx1, nyt * nchunks, P.H % 32 != 1);
     return 0;
 }
 
