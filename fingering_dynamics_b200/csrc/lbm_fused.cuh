@@ -80,29 +80,9 @@ __device__ __forceinline__ void prefetch_l2_bulk(const void *p, unsigned bytes)
 #endif
 
 // ---- bulk asynchronous copies (the TMA engine's 1-D path, cp.async.bulk) completing on an mbarrier ----------
-// solid cell ? psi_wall : s.  In fp64 the plain select compiled to a predicated LDC.64 of the parameter (a 64-bit
-// constant cannot be an instruction operand) whose latency sat in front of the psi shuffles of every column
-// (ncu r2b: 7.5 % of all stall samples on the first consumer); two 32-bit selects take the halves as c[][] operands.
 #ifndef FDLBM_FUSED_PLAIN
 #define FDLBM_FUSED_PLAIN 1  // plain columns run a body without the domain / Zou-He tests, the faces get their own CTAs; 0 for A/B
 #endif
-#ifndef FDLBM_EDGE2_IN_PLAIN
-#define FDLBM_EDGE2_IN_PLAIN 0  // 1 for A/B only: the PLAIN body keeps the in-loop flag load of one-row warps (see edge2 below)
-#endif
-#ifndef FDLBM_WALL_SEL
-#define FDLBM_WALL_SEL 1
-#endif
-__device__ __forceinline__ float pick_wall(unsigned solid, const float &wall, float s) { return solid ? wall : s; }
-__device__ __forceinline__ double pick_wall(unsigned solid, const double &wall, double s)
-{
-#if FDLBM_WALL_SEL
-    const int lo = solid ? __double2loint(wall) : __double2loint(s);
-    const int hi = solid ? __double2hiint(wall) : __double2hiint(s);
-    return __hiloint2double(hi, lo);
-#else
-    return solid ? wall : s;
-#endif
-}
 __device__ __forceinline__ unsigned smem_u32(const void *p) { return (unsigned)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ void mbar_init(void *bar, unsigned count)
 {
@@ -240,8 +220,9 @@ __device__ __forceinline__ void fused_strip(const LbmParams<T> &P, const int yt,
     // A lane that is both (a warp of ONE active row: H % 32 == 1 only) needs a second neighbour row, whose flags it
     // loads in the loop.  The PLAIN body is only launched when no warp is like that and has no such load: ptxas put it
     // on the scoreboard of the look-ahead flag loads and then made the psi shuffles -- which reuse its register --
-    // wait for that scoreboard on EVERY path: a full memory latency per column (ncu r2c: 14 % of all stall samples).
-    const bool edge = edge_lo || edge_hi, edge2 = (!PLAIN || FDLBM_EDGE2_IN_PLAIN) && edge_lo && edge_hi;
+    // wait for that scoreboard on EVERY path: a full memory latency per column (ncu r2c: 14 % of all stall samples;
+    // without it +4.1 %, profiles/r2/r2_ab_edge2.txt; profiles/tools/sass_scoreboards.py checks the SASS for the pattern).
+    const bool edge = edge_lo || edge_hi, edge2 = !PLAIN && edge_lo && edge_hi;
     auto wrap_row = [&](int yy) {  // wrapped global row, or -1 for a ghost row of a y-wall variant
         if (yy < 0 || yy >= H) return P.y_wall ? -1 : (yy < 0 ? yy + H : yy - H);
         return yy;
@@ -336,7 +317,11 @@ __device__ __forceinline__ void fused_strip(const LbmParams<T> &P, const int yt,
         return r.refl | (((r.word >> (yy & 31)) & 1u) << 8);
     };
     // psi_new of the cell (column c, global row yy >= 0 already wrapped, stage row jj) from the g stages
-    auto psi_staged = [&](int c, const int sc, int yy, int jj, unsigned flags, T g[9]) -> T {  // sc = slot(c)
+    // bm / b0 / bp: the g stages of columns c-1 / c / c+1.  The column loop keeps the four stage pointers of columns
+    // x-1 .. x+2 and rotates them instead of recomputing slot * FAM at every use
+    auto stage_of = [&](int c) -> const T * { return gst + slot(c) * FAM; };
+    constexpr int FOFF = NS * FAM;  // the f ring lies FOFF elements behind the g ring, same slots
+    auto psi_staged = [&](int c, const T *bm, const T *b0, const T *bp, int yy, int jj, unsigned flags, T g[9]) -> T {
         if (yy < 0) return P.psi_wall;
         if (!PLAIN) {
             const int gx = P.gx0 + c;
@@ -345,23 +330,24 @@ __device__ __forceinline__ void fused_strip(const LbmParams<T> &P, const int yt,
                 if (gx >= P.W) return P.psi_right;
             }
         }
-        pull_staged<T, PT>(gst + slot_add(sc, -1) * FAM, gst + sc * FAM, gst + slot_add(sc, 1) * FAM, jj, flags & 0xffu, g);
+        pull_staged<T, PT>(bm, b0, bp, jj, flags & 0xffu, g);
         if (!PLAIN && P.zou_he) {
             const int gx = P.gx0 + c;
             if (gx == 0 || gx == P.W - 1) zou_he_g(P, gx, yy, g);
         }
-        const T s = (((g[0] + g[1]) + (g[2] + g[3])) + ((g[4] + g[5]) + (g[6] + g[7]))) + g[8];
-        return pick_wall(flags & 0x100u, P.psi_wall, s);
+        if (flags & 0x100u) return P.psi_wall;
+        return (((g[0] + g[1]) + (g[2] + g[3])) + ((g[4] + g[5]) + (g[6] + g[7]))) + g[8];
     };
     // psi_new of column c on rows y-1, y, y+1 (q_m, q_0, q_p); the pulled g of the own cell is returned
-    auto psi_column = [&](int c, const int sc, unsigned fl_own, unsigned fl_edge, T g[9], T &q_m, T &q_0, T &q_p) {
+    auto psi_column = [&](int c, const T *bm, const T *b0, const T *bp, unsigned fl_own, unsigned fl_edge, T g[9], T &q_m,
+                          T &q_0, T &q_p) {
         q_0 = T(0);
-        if (active) q_0 = psi_staged(c, sc, y, j, fl_own, g);
+        if (active) q_0 = psi_staged(c, bm, b0, bp, y, j, fl_own, g);
         T e1 = T(0), e2 = T(0);
         if (edge) {
             T gh[9];
-            e1 = psi_staged(c, sc, ye1, je1, fl_edge, gh);
-            if (edge2) e2 = psi_staged(c, sc, ye2, je2, decode(load_flags(c, ye2), ye2), gh);
+            e1 = psi_staged(c, bm, b0, bp, ye1, je1, fl_edge, gh);
+            if (edge2) e2 = psi_staged(c, bm, b0, bp, ye2, je2, decode(load_flags(c, ye2), ye2), gh);
         }
         const T dn = __shfl_up_sync(FULL, q_0, 1), up = __shfl_down_sync(FULL, q_0, 1);
         q_m = edge_lo ? e1 : dn;
@@ -392,14 +378,15 @@ __device__ __forceinline__ void fused_strip(const LbmParams<T> &P, const int yt,
     landed(xs - 1);
     landed(xs);
     __syncthreads();
-    psi_column(xs - 1, slot(xs - 1), decode(rf_m1, y), decode(re_m1, ye1), g_b, pm_m, pm_0, pm_p);
+    psi_column(xs - 1, stage_of(xs - 2), stage_of(xs - 1), stage_of(xs), decode(rf_m1, y), decode(re_m1, ye1), g_b, pm_m, pm_0, pm_p);
     __syncthreads();
     prefetch(xs - 1);
     cp_async_wait<D>();  // g column xs+1 has landed
     landed(xs + 1);
     __syncthreads();
     fl_cur = decode(rf_0, y);
-    psi_column(xs, slot(xs), fl_cur, decode(re_0, ye1), g_a, p0_m, p0_0, p0_p);
+    psi_column(xs, stage_of(xs - 1), stage_of(xs), stage_of(xs + 1), fl_cur, decode(re_0, ye1), g_a, p0_m, p0_0, p0_p);
+    const T *b_m = stage_of(xs - 1), *b_0 = stage_of(xs), *b_p = stage_of(xs + 1), *b_pp = stage_of(xs + 2);  // columns x-1 .. x+2
 
     // one column.  sx = slot(x); g_cur = g of column x (in), g_nxt = g of column x+1 (out).  Unrolling this loop was
     // measured on B200 (profiles/r2/r2_ab_unroll.txt, r2_ab_lean1.txt): by 4 with every stage slot a literal -18 % (four
@@ -421,7 +408,7 @@ __device__ __forceinline__ void fused_strip(const LbmParams<T> &P, const int yt,
             // f of column x straight into registers; consumed after the psi phase below
 #if FDLBM_F_STAGED
             if (active)
-                pull_staged<T, PT>(fst + slot_add(sx, -1) * FAM, fst + sx * FAM, fst + slot_add(sx, 1) * FAM, j, fl_cur & 0xffu, f);
+                pull_staged<T, PT>(b_m + FOFF, b_0 + FOFF, b_p + FOFF, j, fl_cur & 0xffu, f);
 #else
             if (active) pull_hp(P, Hp, x, y, 0, fl_cur & 0xffu, f);
 #endif
@@ -442,7 +429,7 @@ __device__ __forceinline__ void fused_strip(const LbmParams<T> &P, const int yt,
         }
         const RawFlags fq2 = active ? load_flags(x + 3, y) : z;  // decoded two iterations from now
         const RawFlags eq2 = edge ? load_flags(x + 3, ye1) : z;
-        psi_column(x + 1, slot_add(sx, 1), fl_nxt, fe_nxt, g_nxt, pp_m, pp_0, pp_p);
+        psi_column(x + 1, b_0, b_p, b_pp, fl_nxt, fe_nxt, g_nxt, pp_m, pp_0, pp_p);
         if (active) {
             if (!PLAIN && P.zou_he) {
                 const int gx_ = P.gx0 + x;
@@ -467,6 +454,10 @@ __device__ __forceinline__ void fused_strip(const LbmParams<T> &P, const int yt,
         fl_cur = fl_nxt;
         fq0 = fq1, fq1 = fq2;
         eq0 = eq1, eq1 = eq2;
+        {   // column x+3 takes the stage of column x-1 (four stages: the pointers only rotate)
+            const T *b_n = NS == 4 ? b_m : stage_of(x + 3);
+            b_m = b_0, b_0 = b_p, b_p = b_pp, b_pp = b_n;
+        }
     };
     for (int x = xs; x < xe; ++x) {
         column(x, slot(x), g_a, g_b);

@@ -41,18 +41,6 @@ namespace fdlbm {
 #ifndef FDLBM_F32_FSTAGED
 #define FDLBM_F32_FSTAGED 1  // the f columns go through a second stage ring (measured +1.5 %); 0: per-thread global loads behind an L2 prefetch
 #endif
-// Sizing experiment for a two-steps-per-pass kernel, never on in the shipped build:
-// FDLBM_F32_MOCK2 = 1 runs the arithmetic of a SECOND step on every column -- f and g pulled from the stages again,
-// psi column, stencils, moments, collision, one more barrier -- and folds its results, scaled by a run-time zero, into
-// the psi carry, so the memory traffic of the pass is unchanged and only the per-warp instruction chain doubles;
-// FDLBM_F32_PADSMEM = bytes of unused shared memory per CTA (what the step-t+1 rings would take: fewer CTAs per SM).
-// 2 x LU / (time of that pass) bounds what temporal blocking can reach from above.
-#ifndef FDLBM_F32_MOCK2
-#define FDLBM_F32_MOCK2 0
-#endif
-#ifndef FDLBM_F32_PADSMEM
-#define FDLBM_F32_PADSMEM 0
-#endif
 namespace f32p {
 
 typedef float2 p2;
@@ -108,7 +96,7 @@ FDLBM_DI float lds_f(const float *p)
 struct Cfg {
     static constexpr int NT = 128, ROWS = 256, HALO = 4, PT = ROWS + 2 * HALO, NS = 4, FAM = 9 * PT;
     static constexpr int RINGS = FDLBM_F32_FSTAGED ? 2 : 1;  // g ring (+ f ring)
-    static constexpr size_t SMEM = (size_t)RINGS * NS * FAM * sizeof(float) + FDLBM_F32_PADSMEM;
+    static constexpr size_t SMEM = (size_t)RINGS * NS * FAM * sizeof(float);
 };
 
 // moments of the cell pair (fingering_periodic.py:123-152, 201-208), packed; see moments() in lbm_device.cuh
@@ -210,7 +198,7 @@ FDLBM_DI void collide2(const LbmParams<float> &P, const Macro2 &m, bool solid0, 
 // order and are tiny (2-3 columns): they slip into the CTA slots the one-wave chunking leaves free.
 // HPC > 0: compile-time row pitch (every population offset is an immediate); HPC == 0: P.Hp
 template <int HPC>
-__global__ void __launch_bounds__(Cfg::NT, FDLBM_F32_PADSMEM > 36000 ? 2 : 3)
+__global__ void __launch_bounds__(Cfg::NT, 3)
     k_fused_f32p(const __grid_constant__ LbmParams<float> P, int nyt, int chunk, int fx0, int fx1, int n_fast)
 {
     typedef float T;
@@ -252,7 +240,6 @@ __global__ void __launch_bounds__(Cfg::NT, FDLBM_F32_PADSMEM > 36000 ? 2 : 3)
     };
     const int ye_lo = wrap_row(yb - 1), ye_hi = wrap_row(yb + 2);
     const int ye = edge_lo ? ye_lo : ye_hi;      // the merged pass: this lane's outer row ...
-    const int je = edge_lo ? jb - 1 : jb + 2;    // ... and its stage row
     const bool e_ghost = ye < 0;                 // ghost row of a y wall: psi_wall, no flags
 
     auto slot = [](int c) { return c & (NS - 1); };
@@ -359,8 +346,12 @@ __global__ void __launch_bounds__(Cfg::NT, FDLBM_F32_PADSMEM > 36000 ? 2 : 3)
     };
 
     // g of the row pair of column c after streaming + bounce-back, straight from the stages
-    auto pull_pair = [&](const T *ring, int c, unsigned b0bits, unsigned b1bits, bool anyb, p2 g[9]) {
-        const T *qm = ring + slot(c - 1) * FAM + jb, *q0 = ring + slot(c) * FAM + jb, *qp = ring + slot(c + 1) * FAM + jb;
+    // qm / q0 / qp: the thread's first row in the stages of columns c-1 / c / c+1.  The column loop keeps these
+    // pointers and rotates them (one address computation per column instead of one per use: the slot arithmetic was
+    // ~70 of the 757 warp instructions per column, ncu r2b)
+    auto stage_row = [&](int c) -> const T * { return gst + slot(c) * FAM + jb; };
+    constexpr int FOFF = NS * FAM;  // the f ring lies FOFF elements behind the g ring, same slots
+    auto pull_pair = [&](const T *qm, const T *q0, const T *qp, unsigned b0bits, unsigned b1bits, bool anyb, p2 g[9]) {
         if (!anyb) {
             g[1] = *reinterpret_cast<const p2 *>(qm + 1 * PT);
             g[3] = *reinterpret_cast<const p2 *>(qp + 3 * PT);
@@ -383,17 +374,17 @@ __global__ void __launch_bounds__(Cfg::NT, FDLBM_F32_PADSMEM > 36000 ? 2 : 3)
         }
         g[0] = lds_v2(q0);  // last: a predicated load is never the tail of its block (see ldg_v2)
     };
-    auto pull_pair_g = [&](int c, unsigned b0bits, unsigned b1bits, bool anyb, p2 g[9]) { pull_pair(gst, c, b0bits, b1bits, anyb, g); };
     // psi_new of column c on the row pair (q) and on its outer neighbours (q_lo, q_hi); every column a fast CTA
     // touches is in the domain and carries no Zou-He rule.  KEEP = false: the pulled g is dropped -- the collision
     // of column c reloads it from the stages one iteration later (pull_pair_g), which is cheaper than 18
     // registers held across the collision of column c-1.
-    auto psi_column = [&](int c, unsigned fl_e, const unsigned fl[2], p2 g[9], p2 &q, T &q_lo, T &q_hi) {
+    auto psi_column = [&](int c, const T *sm_, const T *s0_, const T *sp_, unsigned fl_e, const unsigned fl[2], p2 g[9], p2 &q,
+                          T &q_lo, T &q_hi) {  // sm_ / s0_ / sp_ = stage_row(c-1 / c / c+1)
         q = mk(0.0f, 0.0f);
         const unsigned b0bits = fl[0] & 0xffu, b1bits = fl[1] & 0xffu;
         const bool anyb = __any_sync(FULL, has && ((b0bits | b1bits) != 0u));
         if (has) {
-            pull_pair_g(c, b0bits, b1bits, anyb, g);
+            pull_pair(sm_, s0_, sp_, b0bits, b1bits, anyb, g);
             p2 s = add(add(add(g[0], g[1]), add(g[2], g[3])), add(add(g[4], g[5]), add(g[6], g[7])));
             s = add(s, g[8]);
             q.x = (fl[0] & 0x100u) ? P.psi_wall : s.x;
@@ -401,9 +392,8 @@ __global__ void __launch_bounds__(Cfg::NT, FDLBM_F32_PADSMEM > 36000 ? 2 : 3)
         }
         T e = 0.0f, e2 = 0.0f;
         if (edge) {
-            const T *bm = gst + slot(c - 1) * FAM, *b0 = gst + slot(c) * FAM, *bp = gst + slot(c + 1) * FAM;
-            auto one_row = [&](int jj, unsigned fe) -> T {
-                const T *qm = bm + jj, *q0 = b0 + jj, *qp = bp + jj;
+            auto one_row = [&](int dj, unsigned fe) -> T {  // dj = stage row - jb
+                const T *qm = sm_ + dj, *q0 = s0_ + dj, *qp = sp_ + dj;
                 const unsigned bb = fe & 0xffu;
                 T h[9];
                 if (!bb) {
@@ -423,8 +413,8 @@ __global__ void __launch_bounds__(Cfg::NT, FDLBM_F32_PADSMEM > 36000 ? 2 : 3)
                 const T s = (((h[0] + h[1]) + (h[2] + h[3])) + ((h[4] + h[5]) + (h[6] + h[7]))) + h[8];
                 return (fe & 0x100u) ? P.psi_wall : s;
             };
-            e = e_ghost ? P.psi_wall : one_row(je, fl_e);
-            if (edge2) e2 = ye_hi < 0 ? P.psi_wall : one_row(jb + 2, decode(load_flags(c, ye_hi, 1), ye_hi, 0));
+            e = e_ghost ? P.psi_wall : one_row(edge_lo ? -1 : 2, fl_e);
+            if (edge2) e2 = ye_hi < 0 ? P.psi_wall : one_row(2, decode(load_flags(c, ye_hi, 1), ye_hi, 0));
         }
         const T dn = __shfl_up_sync(FULL, q.y, 1), up = __shfl_down_sync(FULL, q.x, 1);
         q_lo = edge_lo ? e : dn;
@@ -457,15 +447,18 @@ __global__ void __launch_bounds__(Cfg::NT, FDLBM_F32_PADSMEM > 36000 ? 2 : 3)
         landed(xs);
         __syncthreads();
         fl_nxt[0] = decode(rf_m1, yb, 0), fl_nxt[1] = decode(rf_m1, yb, 1);
-        psi_column(xs - 1, decode(re_m1, yef, 0) & e_mask, fl_nxt, g_cur, pm, pm_lo, pm_hi);
+        psi_column(xs - 1, stage_row(xs - 2), stage_row(xs - 1), stage_row(xs), decode(re_m1, yef, 0) & e_mask, fl_nxt, g_cur, pm,
+                   pm_lo, pm_hi);
         __syncthreads();
         prefetch(xs - 1);
         cp_async_wait<D>();
         landed(xs + 1);
         __syncthreads();
         fl_cur[0] = decode(rf_0, yb, 0), fl_cur[1] = decode(rf_0, yb, 1);
-        psi_column(xs, decode(re_0, yef, 0) & e_mask, fl_cur, g_cur, p0, p0_lo, p0_hi);
+        psi_column(xs, stage_row(xs - 1), stage_row(xs), stage_row(xs + 1), decode(re_0, yef, 0) & e_mask, fl_cur, g_cur, p0, p0_lo,
+                   p0_hi);
     }
+    const T *a_m = stage_row(xs - 1), *a_0 = stage_row(xs), *a_p = stage_row(xs + 1), *a_pp = stage_row(xs + 2);  // columns x-1 .. x+2
 
     // ---- running pointers: everything the iteration touches is pointer + immediate -----------------------
 #if !FDLBM_F32_FSTAGED
@@ -493,7 +486,7 @@ __global__ void __launch_bounds__(Cfg::NT, FDLBM_F32_PADSMEM > 36000 ? 2 : 3)
             const unsigned b0bits = fl_cur[0] & 0xffu, b1bits = fl_cur[1] & 0xffu;
             const bool anyb = __any_sync(FULL, has && ((b0bits | b1bits) != 0u));
 #if FDLBM_F32_FSTAGED
-            if (has) pull_pair(fst, x, b0bits, b1bits, anyb, f);
+            if (has) pull_pair(a_m + FOFF, a_0 + FOFF, a_p + FOFF, b0bits, b1bits, anyb, f);
 #else
             if (has) {
                 const T *pmn = pc + dm, *ppl = pc + dp;  // rows yb-1 / yb+2 (wrapped)
@@ -550,7 +543,7 @@ __global__ void __launch_bounds__(Cfg::NT, FDLBM_F32_PADSMEM > 36000 ? 2 : 3)
         }
         {
             p2 gd[9];  // dropped (see psi_column)
-            psi_column(x + 1, fe_nxt, fl_nxt, gd, pp, pp_lo, pp_hi);
+            psi_column(x + 1, a_0, a_p, a_pp, fe_nxt, fl_nxt, gd, pp, pp_lo, pp_hi);
         }
         if (has) {
             const bool s0 = fl_cur[0] & 0x100u, s1 = fl_cur[1] & 0x100u;
@@ -586,40 +579,14 @@ __global__ void __launch_bounds__(Cfg::NT, FDLBM_F32_PADSMEM > 36000 ? 2 : 3)
                 }
             }
         }
-#if FDLBM_F32_MOCK2
-        {   // the arithmetic of a second step on this column (see FDLBM_F32_MOCK2 above); results scaled by zero
-            __syncthreads();  // a real second stage reads what the neighbours' first stage has just written
-            asm volatile("" ::: "memory");
-            const p2 zero = bc((float)(P.gx0 < -1000000));
-            p2 f2[9], g2[9], q2;
-            T q2_lo, q2_hi;
-            const unsigned b0bits = fl_cur[0] & 0xffu, b1bits = fl_cur[1] & 0xffu;
-            const bool anyb = __any_sync(FULL, has && ((b0bits | b1bits) != 0u));
-            unsigned fe2 = fe_nxt;
-            asm volatile("" : "+r"(fe2));
-            psi_column(x, fe2, fl_cur, g2, q2, q2_lo, q2_hi);
-            if (has) {
-                pull_pair(fst, x, b0bits, b1bits, anyb, f2);
-                const bool s0 = fl_cur[0] & 0x100u, s1 = fl_cur[1] & 0x100u;
-                if (!(s0 && s1)) {
-                    T gxa, gya, lapa, gxb, gyb, lapb;
-                    stencil9(q2.x, pp.x, pm.x, q2.y, q2_lo, pp.y, pm.y, pm_lo, pp_lo, gxa, gya, lapa);
-                    stencil9(q2.y, pp.y, pm.y, q2_hi, q2.x, pp_hi, pm_hi, pm.x, pp.x, gxb, gyb, lapb);
-                    Macro2 m2;
-                    moments2(P, f2, q2, mk(gxa, gxb), mk(gya, gyb), mk(lapa, lapb), s0, s1, m2);
-                    collide2(P, m2, s0, s1, f2, g2);
-                }
-                p2 acc = mk(0.0f, 0.0f);
-#pragma unroll
-                for (int i = 0; i < 9; ++i) acc = add(acc, add(f2[i], g2[i]));  // stands in for the 18 stage stores
-                pp = fma2(acc, zero, pp);
-            }
-        }
-#endif
         {   // g of column x+1 for the next iteration's collision (the stages x .. x+2 are still in place)
             const unsigned b0bits = fl_nxt[0] & 0xffu, b1bits = fl_nxt[1] & 0xffu;
             const bool anyb = __any_sync(FULL, has && ((b0bits | b1bits) != 0u));
-            if (has) pull_pair_g(x + 1, b0bits, b1bits, anyb, g_cur);
+            if (has) pull_pair(a_0, a_p, a_pp, b0bits, b1bits, anyb, g_cur);
+        }
+        {   // four stages: column x+3 takes the slot of column x-1, the pointers only rotate
+            const T *a_n = a_m;
+            a_m = a_0, a_0 = a_p, a_p = a_pp, a_pp = a_n;
         }
         pm = p0, p0 = pp;
         pm_lo = p0_lo, pm_hi = p0_hi, p0_lo = pp_lo, p0_hi = pp_hi;

@@ -32,11 +32,22 @@ def main():
     ins = decode(lib, kern)
     ldg_sb = sorted({x["wr"] for x in ins if "LDG" in x["text"] and "LDGSTS" not in x["text"] and x["wr"] != 7})
     print("%d instructions; scoreboards written by LDG: %s" % (len(ins), ldg_sb))
+    # loops = backward branches; an instruction is reported with its innermost enclosing loop
+    loops = []
+    for x in ins:
+        m = re.search(r"\bBRA\S*\s+(?:\S+,\s*)?0x([0-9a-f]+)", x["text"])
+        if m and int(m.group(1), 16) < x["addr"]:
+            loops.append((int(m.group(1), 16), x["addr"]))
+    for a, b in sorted(loops, key=lambda l: l[1] - l[0]):
+        if b - a > 0x800:
+            print("  loop %#x..%#x: %d instructions" % (a, b, (b - a) // 16 + 1))
     n = 0
     for x in ins:
         if op in x["text"] and any((x["wait"] >> b) & 1 for b in ldg_sb):
             n += 1
-            print("  %#07x %-60s wait %s" % (x["addr"], x["text"][:60], format(x["wait"], "06b")))
+            inner = min((l for l in loops if l[0] <= x["addr"] <= l[1]), key=lambda l: l[1] - l[0], default=None)
+            print("  %#07x %-56s wait %s  in loop %s" % (x["addr"], x["text"][:56], format(x["wait"], "06b"),
+                                                         "%#x..%#x" % inner if inner else "-"))
     print("%d %s instructions wait on an LDG scoreboard" % (n, op))
 
 
