@@ -357,6 +357,23 @@ def main():
                        "device-side Compute.__init__ (fdlbm_init_state) + K steps + get_state(psi,rho,ux,uy) (D2H, "
                        "float64, page-locked); wall clock, max over ranks, median of 3 jobs; bytes are the job's transfers "
                        "divided by K (the state stays resident between steps, as in the reference's loop)"}
+        # what the job costs when only psi is read back -- the one field the reference's main() keeps (its frames,
+        # fingering_periodic.py:453,462 / fingering.py:557,565-566); reported next to the headline, not instead of it
+        jobs_psi = []
+        for _ in range(3):
+            barrier()
+            t0 = time.perf_counter()
+            job.eng.set_geometry(job.solid, job.refl, col0=job.lo)
+            job.init()
+            job.runner.step(K)
+            job.runner.get_state(("psi",), out={"psi": out["psi"]})
+            barrier()
+            jobs_psi.append(time.perf_counter() - t0)
+        dtp = float(np.median(allreduce_max(jobs_psi)))
+        e2e["psi_only"] = {"value": H * W * K / dtp / 1e6, "unit": "MLUPS", "job_ms": dtp * 1e3,
+                           "d2h_bytes_per_step": out["psi"].nbytes * world / K,
+                           "note": "the same job reading back psi alone (what the reference's main() keeps per frame); "
+                                   "the 4-field job above is PCIe time for 87 % of its read-back (gpurun_in/e2e_breakdown.py)"}
 
     # ---- further legs --------------------------------------------------------------------------------------
     fp32 = None
