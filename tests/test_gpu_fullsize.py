@@ -1,6 +1,7 @@
 """Parity at BASELINE.json's full sizes through size-independent properties (the oracle would take minutes):
-  * 8192x2048 synthetic porous medium (configs[3]): the fused kernel equals the two-pass kernel BIT FOR BIT
-    (two independent schedules of the same arithmetic; the two-pass one is oracle-checked at small sizes);
+  * 8192x2048 synthetic porous medium (configs[3]) and 32768x8192 (configs[4], one GPU): the fused kernel equals the
+    two-pass kernel BIT FOR BIT (two independent schedules of the same arithmetic; the two-pass one is oracle-checked
+    at small sizes);
   * y-translation equivariance of the y-periodic variant: rolling geometry, state and face profiles by k rows
     rolls the result by k rows, bit for bit;
   * closed box (validation.py variant, x periodic, walls): total mass and total order parameter are conserved.
@@ -35,6 +36,33 @@ def test_fused_equals_twopass_at_8192x2048():
     for k in res["fused"]:
         assert np.array_equal(res["fused"][k], res["twopass"][k]), k
     assert np.isfinite(res["fused"]["psi"]).all() and res["fused"]["rho"][solid == 0].min() > 0.5
+
+
+def test_fused_equals_twopass_at_32768x8192():
+    """BASELINE configs[4], the north-star grid, on ONE GPU (77 GB of lattices per engine, one engine at a time): the
+    fused step (row pitch 8192 compiled in, 64 strips, several waves of column chunks) equals the two-pass kernel bit
+    for bit after 2 steps from the device-side initial state.  The geometry is the generator's 8192 x 4096 window
+    tiled 8 times along x (generating 268 M cells on the host takes half a minute; the seams are just more obstacles)."""
+    from fingering_dynamics_b200 import Engine, synthetic as syn
+    H, W, Wt = 8192, 32768, 4096
+    c = syn.fp_constants(H)
+    s1, r1 = syn.porous_geometry(H, Wt)
+    solid, refl = np.ascontiguousarray(np.tile(s1, (1, W // Wt))), np.ascontiguousarray(np.tile(r1, (1, W // Wt)))
+    res = {}
+    for kernel in ("fused", "twopass"):
+        e = Engine(H, W, tau=c["tau"], gamma=c["gamma"], a=c["a"], kappa=c["kappa"], Eta_n=c["Eta_n"], M=c["M"],
+                   psi_wall=c["psi_wall"], zou_he="fp", inlet_ux=c["inlet_ux"], outlet_ux=c["outlet_ux"], kernel=kernel)
+        e.set_geometry(solid, refl)
+        e.init_state(variant="fp", rho0=c["rho0"])
+        e.step(2)
+        res[kernel] = e.get_state(("psi", "rho"))
+        e.close()
+    for k in ("psi", "rho"):
+        assert np.array_equal(res["fused"][k], res["twopass"][k]), k
+    fluid = solid == 0
+    assert np.isfinite(res["fused"]["psi"]).all() and res["fused"]["rho"][fluid].min() > 0.5
+    # the run has started: the injected phase has moved into the medium and rho is no longer flat
+    assert res["fused"]["rho"][fluid].std() > 0
 
 
 @pytest.mark.parametrize("dtype", ["f64", "f32"])
