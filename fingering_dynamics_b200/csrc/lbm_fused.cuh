@@ -443,7 +443,8 @@ __device__ __forceinline__ void fused_strip(const LbmParams<T> &P, const int yt,
                 moments(P, f, p0_0, gx, gy, lap, m);
                 collide(P, m, f, g_cur);
             }
-            store_cell_hp(P, Hp, x, y, f, g_cur);
+            if (PLAIN) store_cell_at(P.dst, Hp, x, y, f, g_cur);  // no halo push in the plain range (fused_plain_range)
+            else store_cell_hp(P, Hp, x, y, f, g_cur);
             if (!PLAIN && P.zou_he) {  // the next step's Zou-He needs grad psi and mu at the face columns
                 const int gx_ = P.gx0 + x;
                 if (gx_ < 2 || gx_ >= P.W - 2) P.psi_new[cell_idx(Hp, x, y)] = p0_0;
@@ -499,6 +500,11 @@ inline void fused_plain_range(const LbmParams<T> &P, int &fx0, int &fx1)
     if (FDLBM_FUSED_PLAIN && P.H % 32 != 1 && !P.x_periodic) {
         fx0 = 2 - P.gx0 > 0 ? 2 - P.gx0 : 0;
         fx1 = P.W - 3 - P.gx0 < P.Wl ? P.W - 3 - P.gx0 : P.Wl;
+    }
+    if (FDLBM_FUSED_PLAIN && P.H % 32 != 1) {
+        // the halo push into a neighbour's ghost columns (peer stores) is face-CTA work too
+        if (P.peer_lo && fx0 < G) fx0 = G;
+        if (P.peer_hi && fx1 > P.Wl - G) fx1 = P.Wl - G;
         if (fx0 > P.Wl) fx0 = P.Wl;
         if (fx1 < fx0) fx1 = fx0;
     }

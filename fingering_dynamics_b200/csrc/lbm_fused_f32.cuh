@@ -556,7 +556,9 @@ __device__ __forceinline__ void fast_strip(const LbmParams<float> &P, const int 
                 *reinterpret_cast<p2 *>(pd + (ptrdiff_t)i * Hp) = f[i];
                 *reinterpret_cast<p2 *>(pd + (ptrdiff_t)(9 + i) * Hp) = g_cur[i];
             }
-            // halo push: the two edge columns also land in the neighbours' ghost columns (peer stores over NVLink)
+            // halo push: the two edge columns also land in the neighbours' ghost columns (peer stores over NVLink).  It
+            // stays in this loop (the fp64 kernel leaves it to its face CTAs): the face CTAs here run the SCALAR code, whose
+            // rounding order differs from the packed collision, and N slabs must reproduce one slab bit for bit
             if (P.peer_lo && x < G) {
                 T *o = P.peer_lo + lat_idx(Hp, P.peer_lo_Wl + x, 0, yb);
 #pragma unroll
