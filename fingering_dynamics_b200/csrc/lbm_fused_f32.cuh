@@ -198,7 +198,8 @@ FDLBM_DI void collide2(const LbmParams<float> &P, const Macro2 &m, bool solid0, 
 // order and are tiny (2-3 columns): they slip into the CTA slots the one-wave chunking leaves free.
 // HPC > 0: compile-time row pitch (every population offset is an immediate); HPC == 0: P.Hp
 // BULK: every stage of this strip is filled by bulk copies (the common case: no y wrap inside the apron, or all pieces
-// 16-byte multiples); the per-thread cp.async fill paths are then compiled OUT of the column loop -- they made its body
+// 16-byte multiples) and no warp of it has a single active row pair; the per-thread cp.async fill paths and the in-loop
+// flag load of such warps are then compiled OUT of the column loop -- they made its body
 // 25 KB of the 32 KB instruction-cache level (ncu r2d: no_instruction 0.49 stalls per issue against 0.17 in the fp64 kernel)
 template <int HPC, bool BULK>
 __device__ __forceinline__ void fast_strip(const LbmParams<float> &P, const int nyt, const int chunk, const int fx0, const int fx1)
@@ -228,7 +229,9 @@ __device__ __forceinline__ void fast_strip(const LbmParams<float> &P, const int 
     // (shuffles); the first and the last active lane of a warp evaluate theirs themselves, in one merged pass
     const bool edge_lo = has && lane == 0;
     const bool edge_hi = has && (lane == 31 || 2 * (t + 1) >= ny);
-    const bool edge = edge_lo || edge_hi, edge2 = edge_lo && edge_hi;
+    // a lane that is both (a warp with ONE active row pair: ny % 64 == 2) loads the flags of its second outer row inside
+    // the loop; strips without such a warp run the BULK instantiation, which has no such load (cf. edge2 in lbm_fused.cuh)
+    const bool edge = edge_lo || edge_hi, edge2 = !BULK && edge_lo && edge_hi;
     auto wrap_row = [&](int yy) {  // wrapped global row, or -1 for a ghost row of a y-wall variant
         if (yy < 0 || yy >= H) return P.y_wall ? -1 : (yy < 0 ? yy + H : yy - H);
         return yy;
@@ -614,7 +617,7 @@ __global__ void __launch_bounds__(Cfg::NT, 3)
     }
     const int y0 = (int)(blockIdx.x % nyt) * ROWS, ny = min(ROWS, P.H - y0);
     const bool wrap = y0 - HALO < 0 || y0 + ny + HALO > P.H;
-    if (FDLBM_F32_BULK && (!wrap || ((P.H % 4) == 0 && (ny % 4) == 0)))
+    if (FDLBM_F32_BULK && (!wrap || ((P.H % 4) == 0 && (ny % 4) == 0)) && (ny % 64) != 2)
         fast_strip<HPC, true>(P, nyt, chunk, fx0, fx1);
     else
         fast_strip<HPC, false>(P, nyt, chunk, fx0, fx1);
