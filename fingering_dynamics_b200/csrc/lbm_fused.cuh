@@ -5,20 +5,23 @@
 // sum of g pulled from ITS neighbours (two-ring dependency, SURVEY.md finding 5).  Instead of staging
 // psi_new through HBM (+30% traffic), a CTA owns a strip of TY consecutive y and MARCHES along x:
 //
-//   * the g columns are streamed from HBM into a shared-memory stage ring with cp.async (16-byte
-//     chunks, D columns ahead of the compute front): the loads of the next columns are in flight while
-//     the current column is collided, and the strip's neighbours in y are reachable for the psi halo;
-//   * the f columns are pulled straight into registers at the top of the iteration from lines that were
-//     prefetched into L2 two columns ahead (staging f too halves the resident CTAs and measured slower);
-//   * iteration x:  wait for g column x+2 (the only barrier) -> pull g of column x+1 from the stages
-//     (+ bounce-back, Zou-He) -> psi_new(x+1, y); rows y-1 / y+1 arrive by WARP SHUFFLE from the
-//     neighbouring lanes (the two end lanes of a warp evaluate their outer neighbour themselves), the
-//     3x3 psi neighbourhood lives in registers and rotates with x -> moments of column x, stencils,
-//     collide with the g pulled one iteration earlier, store the 18 populations of column x (coalesced).
+//   * the g AND f columns stream from HBM into two shared-memory stage rings (4 stages each, one column ahead of the
+//     compute front) through the bulk-copy engine: one thread issues 18 cp.async.bulk of a whole stage row each,
+//     completion is counted in bytes on the stage's mbarrier; the loads of the next column are in flight while the
+//     current one is collided, and the strip's neighbours in y are reachable for the psi halo (apron rows);
+//   * iteration x:  wait for column x+2's stage (mbarrier) and the one __syncthreads -> issue the fill of column x+3
+//     -> pull f of column x and g of column x+1 from the stages (bounce-back = address select) -> psi_new(x+1, y);
+//     rows y-1 / y+1 arrive by WARP SHUFFLE from the neighbouring lanes (the two end lanes of a warp evaluate their
+//     outer neighbour themselves), the 3x3 psi neighbourhood lives in registers and rotates with x -> moments of
+//     column x, stencils, collide with the g pulled one iteration earlier, store the 18 populations (coalesced);
+//   * two bodies: PLAIN (every column the strip touches is inside the domain, no Zou-He rule, no halo push, no
+//     one-row warp; row pitch a template parameter for H = 2048 / 4096 / 8192) for almost all columns, the general
+//     one for the 2-3 columns next to a face / slab edge, which get their own small CTAs at the end of the grid.
 //
 // Scheduling: one resident wave.  Strips are the fast CTA index, so the CTAs working on the same column
 // range advance in step and the apron rows a strip reads are L2 hits on lines its neighbour streams.
 // The y wrap is resolved when a stage is filled; the x wrap / slab halo comes from the ghost columns.
+// Measured on B200, 8192x2048 fp64: 22.2 GLUPS = 0.99 of the HBM roofline (round 1: 0.89); profiles/README.md.
 #pragma once
 #include <cstdio>
 #include <cstdlib>
@@ -33,7 +36,7 @@ namespace fdlbm {
 #define FDLBM_FUSED_D 1  // NS = 3 + D = 4 stages: a power of two, the slot of a column is c & 3
 #endif
 // resident CTAs per SM the register allocation is bounded for: fp64 needs ~166 registers to stay free of
-// spills (3 CTAs = 12 warps, 48 KB of stages each); fp32 fits 128 registers (4 CTAs)
+// spills (3 CTAs = 12 warps, 76 KB of stages each); the generic fp32 instantiation fits 128 registers (4 CTAs)
 #ifndef FDLBM_FUSED_MINB64
 #define FDLBM_FUSED_MINB64 3
 #endif
@@ -42,9 +45,6 @@ namespace fdlbm {
 #endif
 #ifndef FDLBM_BULK_COPY
 #define FDLBM_BULK_COPY 1  // g stages of interior strips through cp.async.bulk + mbarrier (0: per-thread cp.async only)
-#endif
-#ifndef FDLBM_F_STAGED
-#define FDLBM_F_STAGED 1  // the f columns go through a second stage ring (bulk copies); 0: per-thread loads behind an L2 prefetch (measured 2.8 % slower)
 #endif
 constexpr int FUSED_TY = FDLBM_FUSED_TY;  // rows per strip = threads per CTA
 constexpr int FUSED_D = FDLBM_FUSED_D;    // cp.async prefetch distance in columns
@@ -70,14 +70,6 @@ __device__ __forceinline__ void cp_async_wait()
     asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory");
 }
 __device__ __forceinline__ void prefetch_l2(const void *p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
-// one request for a whole run of bytes (16-byte aligned, a multiple of 16 bytes) instead of one per 128-byte line
-__device__ __forceinline__ void prefetch_l2_bulk(const void *p, unsigned bytes)
-{
-    asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(p), "r"(bytes));
-}
-#ifndef FDLBM_L2_BULK
-#define FDLBM_L2_BULK 0  // 1: the f columns are prefetched into L2 with one bulk request per population
-#endif
 
 // ---- bulk asynchronous copies (the TMA engine's 1-D path, cp.async.bulk) completing on an mbarrier ----------
 #ifndef FDLBM_FUSED_PLAIN
@@ -120,7 +112,7 @@ struct FusedCfg {
     static constexpr int PT = TY + 2 * HALO;              // stage row pitch (elements)
     static constexpr int NS = 3 + FUSED_D;                // stages of the g ring (columns x..x+2+D)
     static constexpr int FAM = 9 * PT;                    // elements of one stage (one family of one column)
-    static constexpr int RINGS = FDLBM_F_STAGED ? 2 : 1;  // g ring (+ f ring)
+    static constexpr int RINGS = 2;                       // g ring + f ring
     static constexpr size_t SMEM = (size_t)(RINGS * NS * FAM) * sizeof(T);
 };
 
@@ -196,7 +188,7 @@ __device__ __forceinline__ void fused_strip(const LbmParams<T> &P, const int yt,
     constexpr unsigned FULL = 0xffffffffu;
     extern __shared__ __align__(16) unsigned char smem_raw[];
     T *gst = reinterpret_cast<T *>(smem_raw);        // [NS][9][PT]
-    T *fst = gst + NS * FAM;                         // [NS][9][PT], FDLBM_F_STAGED only
+    T *fst = gst + NS * FAM;                         // [NS][9][PT]
     __shared__ __align__(8) unsigned long long bars[NS];  // one mbarrier per g stage (bulk-copy path)
     const int t = threadIdx.x, lane = t & 31;
     const int H = P.H, Hp = HPC > 0 ? HPC : P.Hp;
@@ -250,7 +242,7 @@ __device__ __forceinline__ void fused_strip(const LbmParams<T> &P, const int yt,
     }
     __syncthreads();
 
-    // one pipeline step: g column v+2+D (and, FDLBM_F_STAGED, f column v+1+D: f is consumed one column behind g, so
+    // one pipeline step: g column v+2+D (and f column v+1+D: f is consumed one column behind g, so
     // its ring holds x-1..x+1 plus the column in flight); only columns this run reads.  Whenever an f column is
     // fetched a g column is fetched with it, on the same mbarrier / commit group.
     auto prefetch_s = [&](int v, const int scg) {  // scg = slot(v + 2 + D)
@@ -258,7 +250,7 @@ __device__ __forceinline__ void fused_strip(const LbmParams<T> &P, const int yt,
         if (cg >= xs - 2 && cg <= xe + 1) {
             T *stage = gst + scg * FAM;
             const T *col = P.src + lat_idx(Hp, cg, 9, 0);
-            const bool with_f = FDLBM_F_STAGED && cg - 1 >= xs - 1 && cg - 1 <= xe;
+            const bool with_f = cg - 1 >= xs - 1 && cg - 1 <= xe;
             T *fstage = fst + slot_add(scg, -1) * FAM;
             const T *fcol = P.src + lat_idx(Hp, cg - 1, 0, 0);
             if (bulk) {
@@ -405,27 +397,8 @@ __device__ __forceinline__ void fused_strip(const LbmParams<T> &P, const int yt,
         prefetch_s(x, slot_add(sx, 2 + D));  // overwrites the stage of g column x-1: no longer read
         T f[9];
         {
-            // f of column x straight into registers; consumed after the psi phase below
-#if FDLBM_F_STAGED
-            if (active)
-                pull_staged<T, PT>(b_m + FOFF, b_0 + FOFF, b_p + FOFF, j, fl_cur & 0xffu, f);
-#else
-            if (active) pull_hp(P, Hp, x, y, 0, fl_cur & 0xffu, f);
-#endif
-            // and the lines of f column x+L2_AHEAD into L2: one prefetch per 128-byte line of the strip
-            constexpr int LPP = (TY * (int)sizeof(T) + 127) / 128;  // lines per population row
-            const int cf = x + FUSED_L2_AHEAD;
-            const int tt = TY - 1 - t;  // the cp.async issue above kept the low warps busy: use the high ones
-            if (FDLBM_F_STAGED) {
-                // no L2 prefetch: the bulk copy of an f column is itself issued two columns ahead of its use
-            } else if (FDLBM_L2_BULK) {
-                if (FUSED_L2_AHEAD > 0 && tt < 9 && cf <= xe + 1)
-                    prefetch_l2_bulk(P.src + lat_idx(Hp, cf, tt, y0), (unsigned)((ny * (int)sizeof(T) + 15) & ~15));
-            } else if (FUSED_L2_AHEAD > 0 && tt < 9 * LPP && cf <= xe + 1) {
-                const int pop = tt / LPP, ln = tt - pop * LPP;
-                const int yy = y0 + ln * (128 / (int)sizeof(T));
-                if (yy < H) prefetch_l2(P.src + lat_idx(Hp, cf, pop, yy));
-            }
+            // f of column x from its stages into registers; consumed after the psi phase below
+            if (active) pull_staged<T, PT>(b_m + FOFF, b_0 + FOFF, b_p + FOFF, j, fl_cur & 0xffu, f);
         }
         const RawFlags fq2 = active ? load_flags(x + 3, y) : z;  // decoded two iterations from now
         const RawFlags eq2 = edge ? load_flags(x + 3, ye1) : z;

@@ -1,45 +1,43 @@
 // lbm_fused_f32.cuh -- the fused step kernel for fp32 storage: two rows per thread, PACKED arithmetic.
 //
-// Same algorithm as k_fused (lbm_fused.cuh): a CTA owns a strip of rows and marches along x; the g columns
-// stream through a cp.async stage ring, f goes through registers behind an L2 prefetch, psi of the rows above /
-// below arrives by warp shuffle, one barrier per column.  In fp32 the memory time per column is half of fp64's
-// and the step is bound by INSTRUCTION ISSUE (profiles/README.md: k_fused_vec<float> issued 1354 warp
-// instructions per 64-cell warp column, 52 % of them integer / address / control).  This kernel cuts the
-// instruction count:
+// Same algorithm as k_fused (lbm_fused.cuh): a CTA owns a strip of rows and marches along x; the g and f columns
+// stream through two shared-memory stage rings filled by bulk copies (cp.async.bulk + mbarrier, one column ahead),
+// psi of the rows above / below arrives by warp shuffle, one barrier per column.  In fp32 the memory time per
+// column is half of fp64's and the scalar two-row kernel was bound by INSTRUCTION ISSUE (profiles/README.md:
+// k_fused_vec<float> issued 1354 warp instructions per 64-cell warp column, 52 % of them integer / address /
+// control).  This kernel cuts the instruction count:
 //
 //   * a thread owns the aligned row pair (yb, yb+1), both rows live in the two halves of float2 registers and
 //     moments + collision run on the packed fp32 pipe (FFMA2 / FADD2 / FMUL2: one issue slot for two cells);
 //   * the collision is written in its even / odd form over the four direction pairs (i, opp(i)): the even part
 //     of f_eq, g_eq and of the forcing term is shared by both directions of a pair;
-//   * every load / store address is ONE per-thread pointer plus an immediate: running pointers advance by the
-//     column stride, population and row offsets fold into the instruction (the row pitch Hp is a template
-//     parameter for the common heights; Hp = 0 reads it from the parameters and pays one IMAD per access);
+//   * every global address is ONE per-thread pointer plus an immediate: running pointers advance by the column
+//     stride, population and row offsets fold into the instruction (the row pitch Hp is a template parameter for
+//     the common heights; Hp = 0 reads it from the parameters and pays one IMAD per access); the four stage
+//     pointers of columns x-1 .. x+2 rotate instead of being recomputed;
 //   * bounce-back is a pair of complementary predicated loads into the same register ("@p ld bounce; @!p ld
 //     stream"), no address selects; warps without a bounce-back cell take a branch with 8-byte loads;
 //   * the two edge lanes of a warp evaluate their outer neighbour rows in ONE merged pass;
-//   * columns next to the Zou-He faces / outside the domain take the generic scalar iteration (rare).
+//   * the columns next to the Zou-He faces / the domain edge run the scalar code in FACE CTAs of the same grid;
+//   * strips that fill in bulk and have no one-row-pair warp run a LEAN instantiation of the column loop (16.6 KB of
+//     code instead of 25 KB of the 32 KB instruction-cache level).
 //
 // Requires an even grid height (aligned row pairs); odd heights use k_fused_vec.
 //
-// Measured on B200 (8192x2048, same box, two interleaved repetitions; profiles/README.md): this kernel 37.9 GLUPS at
-// the time of these experiments (83 % of the HBM roofline, 38.9 = 85.4 % since; the access pattern itself copies at 93.5 % of memcpy speed, gpurun_in/micro/pattern.cu).
-// Variants that put MORE memory requests in flight were all slower: f loads issued one column ahead -1.6 %
-// (ptxas makes the loop head wait for every global load still in flight, so the stall only moves there); f one
-// column ahead in its own registers with g reloaded from a five-stage ring -4 %; L2 prefetch of f 4 columns ahead
-// -13 %, of g 4 columns ahead -9 %; eight g stages (2 CTAs/SM) -4 %.  Keep the loads late and the ring short.
-// A variant with warp-interleaved rows (lane l owns rows l and l+32: every access 128 contiguous bytes, no shared
-// memory bank conflicts, packed stencils, but two 4-byte stores per population) measured -4 % as well.
-// A skeleton of this kernel with the arithmetic replaced by delays (gpurun_in/micro/skeleton.cu) moves 6.0-6.4 TB/s:
-// the remaining gap to the copy ceiling is the per-warp dependency chain at 12 warps/SM, not the request stream.
+// Measured on B200 (8192x2048; profiles/README.md, profiles/r2/): 41.0 GLUPS = 0.914 of the HBM roofline (round 1:
+// 38.5 = 0.859; the scalar two-row kernel 30.0 = 0.66).  The fp64 kernel reaches 0.99 with the same memory pattern per
+// CTA and column; what keeps fp32 below it is the per-warp instruction chain, about as long as the column's transfer
+// time.  Measured and NOT adopted (round 1 + 2): f loads issued one column ahead -1.6 %; f in its own registers with g
+// reloaded from a five-stage ring -4 %; L2 prefetch of f / g 4 columns ahead -13 % / -9 %, bulk L2 prefetch 1 / 2 / 4
+// columns ahead of the stage fill +1.6 / -6 / -26 %; eight g stages (2 CTAs/SM) -4 %; warp-interleaved rows (no
+// shared-memory bank conflicts, but two 4-byte stores per population) -4 %; flag loads earlier in the column 0 %, no
+// flag loads at all (timing mock) -1.7 %; two steps per pass (mock): upper bound 1.11x before overheads.
 #pragma once
 #include "lbm_fused_vec.cuh"
 
 namespace fdlbm {
 #ifndef FDLBM_F32_BULK
 #define FDLBM_F32_BULK 1  // g stages filled by cp.async.bulk + mbarrier as in k_fused (measured +2.8 % over per-thread cp.async; 0 for A/B)
-#endif
-#ifndef FDLBM_F32_FSTAGED
-#define FDLBM_F32_FSTAGED 1  // the f columns go through a second stage ring (measured +1.5 %); 0: per-thread global loads behind an L2 prefetch
 #endif
 namespace f32p {
 
@@ -54,14 +52,6 @@ FDLBM_DI p2 sub(p2 a, p2 b) { return __ffma2_rn(b, bc(-1.0f), a); }
 
 // v <- bit ? *bounce : *stream, as two complementary predicated loads into one register (no address select;
 // ptxas puts both on one scoreboard and does not serialise them)
-FDLBM_DI float ldg_pick(const float *stream, const float *bounce, unsigned bit)
-{
-    float v;
-    asm volatile("{\n .reg .pred q;\n setp.ne.u32 q, %3, 0;\n @q ld.global.f32 %0, [%2];\n @!q ld.global.f32 %0, [%1];\n}"
-        : "=f"(v)
-        : "l"(stream), "l"(bounce), "r"(bit));
-    return v;
-}
 FDLBM_DI float lds_pick(const float *stream, const float *bounce, unsigned bit)
 {
     float v;
@@ -74,12 +64,6 @@ FDLBM_DI float lds_pick(const float *stream, const float *bounce, unsigned bit)
 // unpredicated loads as volatile asm: they keep their place AFTER the predicated pairs.  ptxas turns a predicated
 // load at the end of a block into "branch around + plain load"; the plain load then no longer pairs with its
 // complement and waits for it (a full memory latency per column, measured) -- so the tail is never a pair.
-FDLBM_DI p2 ldg_v2(const float *p)
-{
-    p2 v;
-    asm volatile("ld.global.v2.f32 {%0, %1}, [%2];" : "=f"(v.x), "=f"(v.y) : "l"(p));
-    return v;
-}
 FDLBM_DI p2 lds_v2(const float *p)
 {
     p2 v;
@@ -95,7 +79,7 @@ FDLBM_DI float lds_f(const float *p)
 
 struct Cfg {
     static constexpr int NT = 128, ROWS = 256, HALO = 4, PT = ROWS + 2 * HALO, NS = 4, FAM = 9 * PT;
-    static constexpr int RINGS = FDLBM_F32_FSTAGED ? 2 : 1;  // g ring (+ f ring)
+    static constexpr int RINGS = 2;  // g ring + f ring
     static constexpr size_t SMEM = (size_t)RINGS * NS * FAM * sizeof(float);
 };
 
@@ -210,7 +194,7 @@ __device__ __forceinline__ void fast_strip(const LbmParams<float> &P, const int 
     static_assert(D == 1 && NS == 4, "stage ring of four columns, one column ahead");
     extern __shared__ __align__(16) unsigned char smem_raw[];
     T *gst = reinterpret_cast<T *>(smem_raw);  // [NS][9][PT]
-    T *fst = gst + NS * FAM;                   // [NS][9][PT], FDLBM_F32_FSTAGED only
+    T *fst = gst + NS * FAM;                   // [NS][9][PT]
     const int t = threadIdx.x, lane = t & 31;
     const int H = P.H, Hp = HPC > 0 ? HPC : P.Hp;
     const ptrdiff_t S = (ptrdiff_t)NPOP * Hp;  // column stride (elements)
@@ -269,14 +253,14 @@ __device__ __forceinline__ void fast_strip(const LbmParams<float> &P, const int 
     constexpr bool bulk = false;
     auto landed = [](int) {};
 #endif
-    // g column v+2+D and (FDLBM_F32_FSTAGED) f column v+1+D: f is consumed one column behind g, its ring holds
+    // g column v+2+D and f column v+1+D: f is consumed one column behind g, its ring holds
     // x-1..x+1 plus the column in flight; an f column always travels with a g column (same mbarrier / commit group)
     auto prefetch = [&](int v) {
         const int cg = v + 2 + D;
         if (cg >= xs - 2 && cg <= xe + 1) {
             T *stage = gst + slot(cg) * FAM + EPC * t;
             const T *col = P.src + lat_idx(Hp, cg, 9, 0);
-            const bool with_f = FDLBM_F32_FSTAGED && cg - 1 >= xs - 1 && cg - 1 <= xe;
+            const bool with_f = cg - 1 >= xs - 1 && cg - 1 <= xe;
             T *fstage = fst + slot(cg - 1) * FAM + EPC * t;
             const T *fcol = P.src + lat_idx(Hp, cg - 1, 0, 0);
 #if FDLBM_F32_BULK
@@ -370,7 +354,7 @@ __device__ __forceinline__ void fast_strip(const LbmParams<float> &P, const int 
             g[7] = mk(lds_pick(qp + 7 * PT + 1, o + 5 * PT, b0bits & 0x40u), lds_pick(qp + 7 * PT + 2, o1 + 5 * PT, b1bits & 0x40u));
             g[8] = mk(lds_pick(qm + 8 * PT + 1, o + 6 * PT, b0bits & 0x80u), lds_pick(qm + 8 * PT + 2, o1 + 6 * PT, b1bits & 0x80u));
         }
-        g[0] = lds_v2(q0);  // last: a predicated load is never the tail of its block (see ldg_v2)
+        g[0] = lds_v2(q0);  // last: a predicated load is never the tail of its block (see lds_v2)
     };
     // psi_new of column c on the row pair (q) and on its outer neighbours (q_lo, q_hi); every column a fast CTA
     // touches is in the domain and carries no Zou-He rule.  KEEP = false: the pulled g is dropped -- the collision
@@ -459,11 +443,6 @@ __device__ __forceinline__ void fast_strip(const LbmParams<float> &P, const int 
     const T *a_m = stage_row(xs - 1), *a_0 = stage_row(xs), *a_p = stage_row(xs + 1), *a_pp = stage_row(xs + 2);  // columns x-1 .. x+2
 
     // ---- running pointers: everything the iteration touches is pointer + immediate -----------------------
-#if !FDLBM_F32_FSTAGED
-    const int dm = (yb - 1 < 0 ? yb - 1 + H : yb - 1) - yb;      // f streams with the periodic wrap (np.roll) ...
-    const int dp = (yb + 2 >= H ? yb + 2 - H : yb + 2) - yb;     // ... whatever the psi ghost rows are
-    const T *pc = P.src + lat_idx(Hp, xs, 0, 0) + yb;            // column x, row yb
-#endif
     T *pd = P.dst + lat_idx(Hp, xs, 0, 0) + yb;
     // flags of column x+3: own pair / this lane's outer row
     const uint8_t *fr_own = P.reflect + cell_idx(Hp, xs + 3, 0) + yb;
@@ -483,52 +462,9 @@ __device__ __forceinline__ void fast_strip(const LbmParams<float> &P, const int 
         {   // f of column x: stream + bounce-back straight into registers
             const unsigned b0bits = fl_cur[0] & 0xffu, b1bits = fl_cur[1] & 0xffu;
             const bool anyb = __any_sync(FULL, has && ((b0bits | b1bits) != 0u));
-#if FDLBM_F32_FSTAGED
             if (has) pull_pair(a_m + FOFF, a_0 + FOFF, a_p + FOFF, b0bits, b1bits, anyb, f);
-#else
-            if (has) {
-                const T *pmn = pc + dm, *ppl = pc + dp;  // rows yb-1 / yb+2 (wrapped)
-                if (!anyb) {
-                    f[1] = *reinterpret_cast<const p2 *>(pc - S + 1 * Hp);
-                    f[3] = *reinterpret_cast<const p2 *>(pc + S + 3 * Hp);
-                    f[2] = mk(pmn[2 * Hp], pc[2 * Hp]);
-                    f[4] = mk(pc[4 * Hp + 1], ppl[4 * Hp]);
-                    f[5] = mk(pmn[-S + 5 * Hp], pc[-S + 5 * Hp]);
-                    f[6] = mk(pmn[S + 6 * Hp], pc[S + 6 * Hp]);
-                    f[7] = mk(pc[S + 7 * Hp + 1], ppl[S + 7 * Hp]);
-                    f[8] = mk(pc[-S + 8 * Hp + 1], ppl[-S + 8 * Hp]);
-                } else {
-                    const T *o = pc, *o1 = pc + 1;
-                    f[1] = mk(ldg_pick(pc - S + 1 * Hp, o + 3 * Hp, b0bits & 0x01u), ldg_pick(pc - S + 1 * Hp + 1, o1 + 3 * Hp, b1bits & 0x01u));
-                    f[2] = mk(ldg_pick(pmn + 2 * Hp, o + 4 * Hp, b0bits & 0x02u), ldg_pick(pc + 2 * Hp, o1 + 4 * Hp, b1bits & 0x02u));
-                    f[3] = mk(ldg_pick(pc + S + 3 * Hp, o + 1 * Hp, b0bits & 0x04u), ldg_pick(pc + S + 3 * Hp + 1, o1 + 1 * Hp, b1bits & 0x04u));
-                    f[4] = mk(ldg_pick(pc + 4 * Hp + 1, o + 2 * Hp, b0bits & 0x08u), ldg_pick(ppl + 4 * Hp, o1 + 2 * Hp, b1bits & 0x08u));
-                    f[5] = mk(ldg_pick(pmn - S + 5 * Hp, o + 7 * Hp, b0bits & 0x10u), ldg_pick(pc - S + 5 * Hp, o1 + 7 * Hp, b1bits & 0x10u));
-                    f[6] = mk(ldg_pick(pmn + S + 6 * Hp, o + 8 * Hp, b0bits & 0x20u), ldg_pick(pc + S + 6 * Hp, o1 + 8 * Hp, b1bits & 0x20u));
-                    f[7] = mk(ldg_pick(pc + S + 7 * Hp + 1, o + 5 * Hp, b0bits & 0x40u), ldg_pick(ppl + S + 7 * Hp, o1 + 5 * Hp, b1bits & 0x40u));
-                    f[8] = mk(ldg_pick(pc - S + 8 * Hp + 1, o + 6 * Hp, b0bits & 0x80u), ldg_pick(ppl - S + 8 * Hp, o1 + 6 * Hp, b1bits & 0x80u));
-                }
-                f[0] = ldg_v2(pc);
-            }
-#endif
         }
         prefetch(x);  // after the f loads: f is what the iteration waits for first (+0.9 %)
-        {   // the lines of f column x+L2_AHEAD into L2: one prefetch per 128-byte line of the strip
-            constexpr int LPP = (ROWS * (int)sizeof(T) + 127) / 128;
-            const int cf = x + FUSED_L2_AHEAD;
-            const int tt = NT - 1 - t;  // the cp.async issue above kept the low warps busy: use the high ones
-            if (FDLBM_F32_FSTAGED) {
-                // no L2 prefetch: the stage fill of an f column is itself issued two columns ahead of its use
-            } else if (FDLBM_L2_BULK) {
-                if (FUSED_L2_AHEAD > 0 && tt < 9 && cf <= xe + 1)
-                    prefetch_l2_bulk(P.src + lat_idx(Hp, cf, tt, y0),
-                                     (unsigned)((min(ROWS, H - y0) * (int)sizeof(T) + 15) & ~15));
-            } else if (FUSED_L2_AHEAD > 0 && tt < 9 * LPP && cf <= xe + 1) {
-                const int pop = tt / LPP, ln = tt - pop * LPP;
-                const int yy = y0 + ln * (128 / (int)sizeof(T));
-                if (yy < H) prefetch_l2(P.src + lat_idx(Hp, cf, pop, yy));
-            }
-        }
         // flags of column x+3 (decoded two iterations from now); the flag arrays carry one spare column
         RawFlags fq2 = z, eq2 = z;
         if (has) {
@@ -593,9 +529,6 @@ __device__ __forceinline__ void fast_strip(const LbmParams<float> &P, const int 
         fl_cur[0] = fl_nxt[0], fl_cur[1] = fl_nxt[1];
         fq0 = fq1, fq1 = fq2;
         eq0 = eq1, eq1 = eq2;
-#if !FDLBM_F32_FSTAGED
-        pc += S;
-#endif
         pd += S;
         fr_own += Hp, fr_edge += Hp;
         fs_own += Hp >> 5, fs_edge += Hp >> 5;
