@@ -72,6 +72,9 @@ __device__ __forceinline__ void cp_async_wait()
 __device__ __forceinline__ void prefetch_l2(const void *p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
 
 // ---- bulk asynchronous copies (the TMA engine's 1-D path, cp.async.bulk) completing on an mbarrier ----------
+#ifndef FDLBM_MIN_CHUNK
+#define FDLBM_MIN_CHUNK 2  // shortest column chunk of a CTA: small grids are bound by the per-column chain x columns per CTA, so they get many short CTAs (400x400: 22.5 -> 18.4 us per step, 200x250: 29.8 -> 20.5)
+#endif
 #ifndef FDLBM_FUSED_PLAIN
 #define FDLBM_FUSED_PLAIN 1  // plain columns run a body without the domain / Zou-He tests, the faces get their own CTAs; 0 for A/B
 #endif
@@ -486,13 +489,13 @@ inline void fused_plain_range(const LbmParams<T> &P, int &fx0, int &fx1)
 // Column chunk length for `nyt` strips on `n_cta` resident CTA slots.  With c chunks per strip the kernel takes
 // ceil(nyt*c / n_cta) waves of Wl/c columns each; pick the c that minimises waves/c (one wave when the strips
 // divide the slots well, a few shorter waves for tall grids); the 3-column pipeline warm-up of every chunk is in the
-// cost.  Small grids (the reference's own 400x400 / 380x380 / 200x250) get chunks as short as 8 columns: filling the
-// SMs matters more than the warm-up there (400x400 fp64: 176 -> 25 us per step).
+// cost.  Small grids (the reference's own 400x400 / 380x380 / 200x250) get chunks as short as 2 columns: filling the
+// SMs matters more than the warm-up there (400x400 fp64: 176 -> 25 us per step with 8-column chunks in round 1, 18 us now).
 inline int fused_chunk(int nyt, int n_cta, int Wl)
 {
     int best_c = 1;
     double best = 1e30;
-    const int c_max = Wl / 8 > 1 ? Wl / 8 : 1;
+    const int c_max = Wl / FDLBM_MIN_CHUNK > 1 ? Wl / FDLBM_MIN_CHUNK : 1;
     for (int c = 1; c <= c_max && c <= 4096; ++c) {
         const int waves = (nyt * c + n_cta - 1) / n_cta;
         const double cost = (double)waves / c * (1.0 + 3.0 * c / Wl);
@@ -502,7 +505,7 @@ inline int fused_chunk(int nyt, int n_cta, int Wl)
         }
     }
     int chunk = (Wl + best_c - 1) / best_c;
-    return chunk < 8 ? 8 : chunk;
+    return chunk < FDLBM_MIN_CHUNK ? FDLBM_MIN_CHUNK : chunk;
 }
 
 // returns 0 or a cudaError_t
