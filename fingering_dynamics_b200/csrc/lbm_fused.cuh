@@ -183,6 +183,17 @@ struct RawFlags {
 // PLAIN: every column the strip touches (xs-1 .. xe+1) is inside the domain and carries no Zou-He rule, so the
 // per-column domain / face tests (and the loads of W, gx0, psi_left, psi_right they need: 24 LDC per warp and column
 // in the one-body kernel) are compiled out; the face columns run the general body in their own small CTAs.
+// all stages of the strip starting at row y0 can be filled by bulk copies: no y wrap inside the apron, or every piece a
+// 16-byte multiple
+template <typename T, int TY>
+__device__ __forceinline__ bool fused_bulk_strip(int H, int y0)
+{
+    constexpr int HALO = FusedCfg<T, TY>::HALO;
+    const int ny = min(TY, H - y0);
+    const bool wrap = y0 - HALO < 0 || y0 + TY + HALO > H;
+    return FDLBM_BULK_COPY && (!wrap || ((H * sizeof(T)) % 16 == 0 && (ny * sizeof(T)) % 16 == 0));
+}
+
 template <typename T, int TY, int HPC, bool PLAIN>
 __device__ __forceinline__ void fused_strip(const LbmParams<T> &P, const int yt, const int xs, const int xe)
 {
@@ -237,7 +248,9 @@ __device__ __forceinline__ void fused_strip(const LbmParams<T> &P, const int yt,
     // the pieces keep the 16-byte granularity; the kernel ends with its slowest CTA, and strips on the per-thread path
     // were that CTA.
     const bool wrap_lo = y0 - HALO < 0, wrap_hi = y0 + TY + HALO > H;  // CTA-uniform
-    const bool bulk = FDLBM_BULK_COPY && ((!wrap_lo && !wrap_hi) || ((H * sizeof(T)) % 16 == 0 && (ny * sizeof(T)) % 16 == 0));
+    // the PLAIN body is only launched for strips whose stages all fill in bulk (fused_bulk_strip): the per-thread fill path is
+    // then compiled out of its column loop
+    const bool bulk = PLAIN || fused_bulk_strip<T, TY>(H, y0);
     if (t == 0) {
 #pragma unroll
         for (int s_ = 0; s_ < NS; ++s_) mbar_init(&bars[s_], 1);
@@ -461,7 +474,7 @@ __global__ void __launch_bounds__(TY, sizeof(T) == 8 ? FDLBM_FUSED_MINB64 : FDLB
     } else {
         yt = (int)blockIdx.x % nyt, xs = fx0 + ((int)blockIdx.x / nyt) * chunk, xe = min(fx1, xs + chunk);
     }
-    if (FDLBM_FUSED_PLAIN && plain_ok && !face)
+    if (FDLBM_FUSED_PLAIN && plain_ok && !face && fused_bulk_strip<T, TY>(P.H, yt * TY))
         fused_strip<T, TY, HPC, true>(P, yt, xs, xe);
     else
         fused_strip<T, TY, HPC, false>(P, yt, xs, xe);
