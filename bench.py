@@ -52,6 +52,27 @@ def peak_hbm():
         return 6650.0, "fallback (B200_PROFILING.md)"
 
 
+def copy_bandwidth_here():
+    """this box's own copy bandwidth, measured the way MEASURED_PEAKS.json says the pod's was (b.copy_(a) over 1 Gi bf16
+    elements, read + write bytes, best of 10, CUDA events): boxes differ from the pod figure by a few per cent"""
+    import torch
+    try:
+        a = torch.empty(1 << 30, dtype=torch.bfloat16, device="cuda")
+        b = torch.empty_like(a)
+        best = 0.0
+        for _ in range(12):
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            b.copy_(a)
+            e1.record()
+            torch.cuda.synchronize()
+            best = max(best, 2 * a.numel() * 2 / (e0.elapsed_time(e1) * 1e-3) / 1e9)
+        del a, b
+        return best
+    except Exception:
+        return None
+
+
 class ClockSampler:
     """nvidia-smi SM clocks / throttle reasons sampled during the timed region."""
     Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
@@ -406,6 +427,7 @@ def main():
         return
 
     peak, how = peak_hbm()
+    here = copy_bandwidth_here() if extras else None
     step_ms = ms / K
     achieved = B_ALG[args.dtype] * cells_local / (step_ms * 1e-3) / 1e9
     traffic, traffic_note = lookup_traffic(args.dtype, cells_local // H, H) if world == 1 else \
@@ -429,10 +451,13 @@ def main():
             "clocks": clocks.summary(th0, th1), "gpu_launches": launches, "e2e": e2e,
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                          "traffic": traffic, "traffic_note": traffic_note, "peak_source": how,
+                         "copy_gbs_this_box": here, "frac_of_this_box": None if not here else achieved / here,
                          "frac_sustained": None if sustained is None else
                          B_ALG[args.dtype] * cells_local / (sustained["ms_per_step"] * 1e-3) / 1e9 / peak,
                          "note": "achieved = %.0f B/LU x %d LU per launch / mean launch duration (CUDA events over the median "
-                                 "timed window); burst figure (windows of K steps), frac_sustained from the >= 2 s window"
+                                 "timed window); burst figure (windows of K steps), frac_sustained from the >= 2 s window; "
+                                 "peak is the pod's recorded copy bandwidth, copy_gbs_this_box the same copy measured on this "
+                                 "box after the timed region (boxes differ by a few per cent, so frac can touch 1)"
                                  % (B_ALG[args.dtype], cells_local)},
             "fluid_fraction": fluid_fraction}
     if sustained is not None:
