@@ -7,6 +7,7 @@
 #include <cstdlib>
 #include <cstring>
 #include <unistd.h>
+#include <functional>
 #include <mutex>
 #include <string>
 #include <vector>
@@ -226,7 +227,7 @@ int wrap_ghosts(fdlbm_engine *e, void *lat)
 }
 
 template <typename T>
-int launch_step(fdlbm_engine *e, bool finalize)
+int launch_step(fdlbm_engine *e, bool finalize, const std::function<int()> &between = nullptr)
 {
     LbmParams<T> P = make_params<T>(e, e->cur, e->pcur);
     if (e->cfg.x_periodic && !e->cfg.external_halo) {
@@ -237,11 +238,17 @@ int launch_step(fdlbm_engine *e, bool finalize)
     if (!finalize && e->peer_mode()) set_peers(e, P, 1 - e->cur);
     if (finalize || e->kernel == FDLBM_KERNEL_TWOPASS) {
         k_psi<T><<<cell_grid(e, hi - lo), TPB, 0, e->stream>>>(P, lo);
-        if (finalize)
+        e->launches += 1;
+        if (finalize) {
+            // psi is complete after the first pass: its download (transpose on this stream, copy on the copy stream)
+            // is queued before the field pass, so the PCIe transfer of psi runs while the fields are computed
+            int rc = between ? between() : 0;
+            if (rc) return rc;
             k_step_twopass<T, true><<<cell_grid(e, e->Wl), TPB, 0, e->stream>>>(P, field_ptrs<T>(e));
-        else
+        } else {
             k_step_twopass<T, false><<<cell_grid(e, e->Wl), TPB, 0, e->stream>>>(P, field_ptrs<T>(e));
-        e->launches += 2;
+        }
+        e->launches += 1;
     } else {
         int rc = launch_fused_auto<T>(P, e->stream);
         if (rc) return fail(FDLBM_E_CUDA, "fused launch configuration failed (%d)", rc);
@@ -407,6 +414,7 @@ int get_state_t(fdlbm_engine *e, int col0, int ncw, const fdlbm_fields *out)
     int rc = ensure_fields(e);
     if (rc) return rc;
     const T *lat, *psi;
+    bool psi_done = false;
     if (e->state == ST_PRE) {
         lat = (const T *)e->lat[e->cur];
         psi = (const T *)e->psi[e->pcur];
@@ -421,15 +429,20 @@ int get_state_t(fdlbm_engine *e, int col0, int ncw, const fdlbm_fields *out)
             k_psi<T><<<cell_grid(e, e->Wl), TPB, 0, e->stream>>>(P, 0);
             CU(cudaGetLastError());
             e->launches += 1;
-        } else if ((rc = launch_step<T>(e, true))) {  // writes lat[1-cur], psi[1-pcur], fields; no swap
-            return rc;
+        } else {  // writes lat[1-cur], psi[1-pcur], fields; no swap
+            const T *psi_new = (const T *)e->psi[1 - e->pcur];
+            rc = launch_step<T>(e, true, [&]() {
+                psi_done = true;
+                return download_planes<T>(e, out->psi, 1, col0, ncw, psi_new, 0, Hp);
+            });
+            if (rc) return rc;
         }
         lat = (const T *)e->lat[1 - e->cur];
         psi = (const T *)e->psi[1 - e->pcur];
     }
     if ((rc = download_planes<T>(e, out->f, 9, col0, ncw, lat, Hp, (size_t)NPOP * Hp))) return rc;
     if ((rc = download_planes<T>(e, out->g, 9, col0, ncw, lat + 9 * Hp, Hp, (size_t)NPOP * Hp))) return rc;
-    if ((rc = download_planes<T>(e, out->psi, 1, col0, ncw, psi, 0, Hp))) return rc;
+    if (!psi_done && (rc = download_planes<T>(e, out->psi, 1, col0, ncw, psi, 0, Hp))) return rc;
     const T *fb = (const T *)e->fields;
     double *dsts[9] = {out->rho, out->ux, out->uy, out->p, out->mu, out->mix_tau, out->nabla_psix, out->nabla_psiy,
                        out->nabla_psi2};
