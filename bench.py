@@ -394,7 +394,7 @@ def main():
         e2e["psi_only"] = {"value": H * W * K / dtp / 1e6, "unit": "MLUPS", "job_ms": dtp * 1e3,
                            "d2h_bytes_per_step": out["psi"].nbytes * world / K,
                            "note": "the same job reading back psi alone (what the reference's main() keeps per frame); "
-                                   "the 4-field job above is PCIe time for 87 % of its read-back (gpurun_in/e2e_breakdown.py)"}
+                                   "the read-back of the 4-field job above is 96 % PCIe time (4 x 2.37 ms of 9.9 ms, gpurun_in/e2e_breakdown.py)"}
 
     # ---- further legs --------------------------------------------------------------------------------------
     fp32 = None
